@@ -1,0 +1,110 @@
+// TEST INFRASTRUCTURE -- C API over the transliterated reference decoder (see build_ref.py).
+// Mirrors the call sequence of the reference's callers (MobiConverter/Program.cs:64-71, 243-245):
+//   d = new MobiclipDecoder(W, H, Version); d.Data = bytes; d.Offset = off; bmp = d.DecodeFrame();
+#include "ref_shim.h"
+#include "gen_IOUtil.h"
+using namespace LibMobiclip_Utils;
+#include "gen_MobiConst.h"
+#include "gen_MobiclipDecoder.h"
+
+using LibMobiclip_Codec_Mobiclip::MobiclipDecoder;
+
+extern "C" {
+
+void* mobiref_create(unsigned w, unsigned h, int version /*0 VxDS, 1 ModsDS, 2 Moflex3DS*/) {
+    return new MobiclipDecoder(w, h, (MobiclipDecoder::MobiclipVersion)version);
+}
+
+void mobiref_destroy(void* h) { delete (MobiclipDecoder*)h; }
+
+// Returns 1 when DecodeFrame() returned a Bitmap, 0 when it returned null (frame aborted).
+// bgra (optional) receives W*H*4 bytes in memory order B,G,R,A.
+int mobiref_decode(void* h, const uint8_t* data, int len, int* offset_inout, uint8_t* bgra) {
+    MobiclipDecoder* d = (MobiclipDecoder*)h;
+    d->Data = Arr<byte>::New(len);
+    if (len) std::memcpy(d->Data.raw(), data, (size_t)len);
+    d->Offset = *offset_inout;
+    Bitmap b = d->DecodeFrame();
+    *offset_inout = d->Offset;
+    if (b.IsNull()) return 0;
+    if (bgra) std::memcpy(bgra, b.px->data(), b.px->size());
+    return 1;
+}
+
+// Copies the strided planes Y[0] (Stride*H) and UV[0] (Stride*H/2) exactly as the reference holds them.
+int mobiref_planes(void* h, uint8_t* y, uint8_t* uv) {
+    MobiclipDecoder* d = (MobiclipDecoder*)h;
+    if (!d->Y[0].p || !d->UV[0].p) return 0;
+    if (y) std::memcpy(y, d->Y[0].raw(), (size_t)d->Y[0].Length);
+    if (uv) std::memcpy(uv, d->UV[0].raw(), (size_t)d->UV[0].Length);
+    return 1;
+}
+
+int mobiref_stride(void* h) { return ((MobiclipDecoder*)h)->Stride; }
+unsigned mobiref_quantizer(void* h) { return ((MobiclipDecoder*)h)->Quantizer; }
+unsigned mobiref_yuvformat(void* h) { return ((MobiclipDecoder*)h)->YuvFormat; }
+
+}  // extern "C"
+
+// ---- primitive-level hooks for differential unit tests (tests/test_oracle_primitives.py) ----
+extern "C" {
+// Allocate fresh Y[0]/UV[0] and fill them from caller buffers (Stride*H and Stride*H/2 bytes).
+void mobiref_set_planes(void* h, const uint8_t* y, const uint8_t* uv) {
+    MobiclipDecoder* d = (MobiclipDecoder*)h;
+    d->Y[0] = Arr<byte>::New(d->Stride * d->Height);
+    d->UV[0] = Arr<byte>::New(d->Stride * d->Height / 2);
+    std::memcpy(d->Y[0].raw(), y, (size_t)d->Y[0].Length);
+    std::memcpy(d->UV[0].raw(), uv, (size_t)d->UV[0].Length);
+}
+// PredictIntra (MD:1883) on Y[0] (plane=0) or UV[0] (plane=1); `window` primes the bit window
+// (modes 2/12 read a signed Elias-gamma delta from it).  Returns 0 if the reference threw.
+int mobiref_predict_intra(void* h, unsigned mode, int plane, int offset, unsigned window) {
+    MobiclipDecoder* d = (MobiclipDecoder*)h;
+    d->Data = Arr<byte>::New(0);
+    d->Offset = 0;
+    int nbits = 16;
+    uint r3 = window;
+    try { d->PredictIntra(nbits, r3, mode, plane ? d->UV[0] : d->Y[0], offset); } catch (...) { return 0; }
+    return 1;
+}
+// 16x16 plane predictor sub_1167BC (MD:3017)
+int mobiref_plane16(void* h, int offset, unsigned window) {
+    MobiclipDecoder* d = (MobiclipDecoder*)h;
+    d->Data = Arr<byte>::New(0);
+    d->Offset = 0;
+    int nbits = 16;
+    uint r3 = window;
+    try { d->sub_1167BC(d->Y[0], offset, nbits, r3); } catch (...) { return 0; }
+    return 1;
+}
+// CopyBlock (MD:418): Src = caller plane copy of Y[0]/UV[0] size, Dst = Y[0] / UV[0]
+int mobiref_copy_block(void* h, int plane, const uint8_t* src, int dx, int dy, unsigned w, unsigned hgt, int offset) {
+    MobiclipDecoder* d = (MobiclipDecoder*)h;
+    Arr<byte>& dst = plane ? d->UV[0] : d->Y[0];
+    Arr<byte> s = Arr<byte>::New(dst.Length);
+    std::memcpy(s.raw(), src, (size_t)dst.Length);
+    try { d->CopyBlock(s, dx, dy, w, hgt, dst, offset); } catch (...) { return 0; }
+    return 1;
+}
+// The size-dispatched inverse transforms exactly as loc_116540 / sub_1166E8 pick them (MD:2939-2942,
+// 2954-2955): coef = 64 or 16 s32 in Internal[90..] order, endpos = scan position after the last coefficient.
+int mobiref_idct(void* h, int plane, int n, const int32_t* coef, int endpos, int offset) {
+    MobiclipDecoder* d = (MobiclipDecoder*)h;
+    Arr<byte>& dst = plane ? d->UV[0] : d->Y[0];
+    for (int i = 0; i < n * n; i++) d->Internal[90 + i] = (uint)coef[i];
+    try {
+        if (n == 8) {
+            uint r12 = 10 + endpos;
+            if (r12 <= 11) d->IDCT1Px8(dst, offset);
+            else if (r12 <= 13) d->IDCT3Px8(dst, offset);
+            else if (r12 <= 20) d->IDCT16Px8(dst, offset);
+            else d->IDCT64Px8(dst, offset);
+        } else {
+            uint r12 = 74 + endpos;
+            if (r12 <= 75) d->IDCT1Px4(dst, offset);
+            else d->IDCT16Px4(dst, offset);
+        }
+    } catch (...) { return 0; }
+    return 1;
+}
+}  // extern "C"
