@@ -1,0 +1,635 @@
+// Mobiclip reconstruction kernels for sm_100a.  "MD:n" = LibMobiclip/Codec/Mobiclip/MobiclipDecoder.cs:n.
+//
+// Data layout in HBM (identical to the reference's managed arrays so that its flat, unclamped
+// addressing falls out for free): a picture is Stride*H luma bytes followed by Stride*H/2 chroma
+// bytes, U in columns [0,Stride/2) and V in [Stride/2,Stride) of each chroma row (MD:107-108, 267-268).
+// Stride padding is zero and never written.
+//
+// k_inter : one warp per 16x16 macroblock.  Lane l owns luma row l/2, 8 pixels (one 64-bit store) and
+//           chroma plane l/16, row (l/2)%8, 4 pixels (one 32-bit store).  Motion compensation works
+//           on packed bytes (4 pixels per ALU op, truncating averages MD:418-456); the inverse
+//           transforms run one 8-point (or two 4-point) butterflies per lane with the transpose
+//           through a per-warp shared-memory tile, laid out so that the lane that finishes a row of
+//           residuals is the lane that owns those pixels.
+// k_intra : one warp per intra macroblock, executed in decode order through an atomic ticket; the
+//           neighbourhood (row above incl. top-right, column left, and the not-yet-decoded pixels to
+//           the right, which the reference reads as 0 from its freshly allocated planes MD:107) is
+//           staged in shared memory, availability decided by coordinates, never by memory contents.
+// No tensor cores: these are 8-bit fixed-point butterflies and byte shuffles, bound by HBM/LSU.
+#include "mobi_kernels.h"
+
+namespace mobi {
+namespace {
+
+constexpr int INTER_WARPS = 8;
+constexpr int INTRA_WARPS = 4;
+
+// ------------------------------------------------------------------------------------------------
+// shared arithmetic
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t half4(uint32_t x) { return (x >> 1) & 0x7f7f7f7fu; }
+
+__device__ __forceinline__ void bfly8(const int32_t in[8], int32_t out[8]) {  // MD:3452-3485
+    int32_t a0 = in[0] + in[4], a1 = in[0] - in[4], a2 = in[2] + (in[6] >> 1), a3 = (in[2] >> 1) - in[6];
+    int32_t e0 = a0 + a2, e3 = a0 - a2, e1 = a1 + a3, e2 = a1 - a3;
+    int32_t b0 = in[1] + in[7] - in[3] - (in[3] >> 1), b1 = in[7] - in[1] + in[5] + (in[5] >> 1);
+    int32_t b2 = in[5] - (in[7] + (in[7] >> 1)) - in[3], b3 = in[3] + in[5] + in[1] + (in[1] >> 1);
+    int32_t o1 = b2 + (b3 >> 2), o7 = b3 - (b2 >> 2), o3 = b0 + (b1 >> 2), o5 = (b0 >> 2) - b1;
+    out[0] = e0 + o7; out[7] = e0 - o7; out[1] = e1 + o5; out[6] = e1 - o5;
+    out[2] = e2 + o3; out[5] = e2 - o3; out[3] = e3 + o1; out[4] = e3 - o1;
+}
+__device__ __forceinline__ void bfly4(const int32_t in[4], int32_t out[4]) {  // MD:3740-3747
+    int32_t s = in[0] + in[2], d = in[0] - in[2], p = (in[1] >> 1) - in[3], q = in[1] + (in[3] >> 1);
+    out[0] = s + q; out[3] = s - q; out[1] = d + p; out[2] = d - p;
+}
+__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }  // Vx2MinMaxTable, MobiConst.cs:587
+__device__ __forceinline__ uint32_t addclip4(uint32_t px, const int32_t* r) {  // r = transform outputs before >>6
+    uint32_t o = (uint32_t)clip255((int)(px & 255u) + (r[0] >> 6));
+    o |= (uint32_t)clip255((int)((px >> 8) & 255u) + (r[1] >> 6)) << 8;
+    o |= (uint32_t)clip255((int)((px >> 16) & 255u) + (r[2] >> 6)) << 16;
+    o |= (uint32_t)clip255((int)(px >> 24) + (r[3] >> 6)) << 24;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// motion compensation primitives (CopyBlock MD:418-456)
+// ------------------------------------------------------------------------------------------------
+// 8 (or 4) consecutive bytes at an arbitrary address, plus the same run one byte further on.
+__device__ __forceinline__ void ld_row8(const uint8_t* p, uint32_t& a0, uint32_t& a1, uint32_t& b0, uint32_t& b1) {
+    uintptr_t ad = (uintptr_t)p;
+    uint32_t sh = ((uint32_t)ad & 3u) * 8u;
+    const uint32_t* q = (const uint32_t*)(ad & ~(uintptr_t)3);
+    uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    a0 = __funnelshift_r(w0, w1, sh); a1 = __funnelshift_r(w1, w2, sh);
+    b0 = __funnelshift_rc(w0, w1, sh + 8u); b1 = __funnelshift_rc(w1, w2, sh + 8u);
+}
+__device__ __forceinline__ void ld_row4(const uint8_t* p, uint32_t& a0, uint32_t& b0) {
+    uintptr_t ad = (uintptr_t)p;
+    uint32_t sh = ((uint32_t)ad & 3u) * 8u;
+    const uint32_t* q = (const uint32_t*)(ad & ~(uintptr_t)3);
+    uint32_t w0 = __ldg(q), w1 = __ldg(q + 1);
+    a0 = __funnelshift_r(w0, w1, sh);
+    b0 = __funnelshift_rc(w0, w1, sh + 8u);
+}
+__device__ __forceinline__ void mc_row8(const uint8_t* p, int S, int phase, uint32_t& o0, uint32_t& o1) {
+    uint32_t a0, a1, b0, b1;
+    ld_row8(p, a0, a1, b0, b1);
+    if (phase == 0) { o0 = a0; o1 = a1; return; }
+    if (phase == 1) { o0 = half4(a0) + half4(b0); o1 = half4(a1) + half4(b1); return; }
+    uint32_t c0, c1, d0, d1;
+    ld_row8(p + S, c0, c1, d0, d1);
+    if (phase == 2) { o0 = half4(a0) + half4(c0); o1 = half4(a1) + half4(c1); return; }
+    o0 = half4(half4(a0) + half4(b0)) + half4(half4(c0) + half4(d0));
+    o1 = half4(half4(a1) + half4(b1)) + half4(half4(c1) + half4(d1));
+}
+__device__ __forceinline__ uint32_t mc_row4(const uint8_t* p, int S, int phase) {
+    uint32_t a0, b0;
+    ld_row4(p, a0, b0);
+    if (phase == 0) return a0;
+    if (phase == 1) return half4(a0) + half4(b0);
+    uint32_t c0, d0;
+    ld_row4(p + S, c0, d0);
+    if (phase == 2) return half4(a0) + half4(c0);
+    return half4(half4(a0) + half4(b0)) + half4(half4(c0) + half4(d0));
+}
+__device__ __forceinline__ uint32_t mc_px(const uint8_t* p, int S, int phase) {
+    uint32_t a = __ldg(p);
+    if (phase == 0) return a;
+    if (phase == 1) return (a >> 1) + (__ldg(p + 1) >> 1);
+    if (phase == 2) return (a >> 1) + (__ldg(p + S) >> 1);
+    return (((a >> 1) + (__ldg(p + 1) >> 1)) >> 1) + (((__ldg(p + S) >> 1) + (__ldg(p + S + 1) >> 1)) >> 1);
+}
+struct PartV { int mvx, mvy, ref; };
+__device__ __forceinline__ PartV ld_part(const mobi_part* p) {
+    uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
+    PartV v;
+    v.mvx = (int)(int16_t)(w.x >> 16);
+    v.mvy = (int)(int16_t)(w.y & 0xFFFFu);
+    v.ref = (int)((w.x >> 12) & 15u);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// inter macroblocks
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DevJob* __restrict__ jobs, Geom g) {
+    __shared__ uint32_t s_qtab[80];
+    __shared__ __align__(16) int32_t s_coef[INTER_WARPS][6 * 64];
+    __shared__ __align__(4) uint8_t s_map[INTER_WARPS][64];
+
+    const DevJob& J = jobs[blockIdx.y];
+    if (J.n_intra == J.n_mb) return;  // I-frame: nothing for this kernel
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 80) s_qtab[threadIdx.x] = __ldg(&J.hdr->qtab[threadIdx.x]);
+    __syncthreads();
+    const uint32_t mb = blockIdx.x * INTER_WARPS + warp;
+    if (mb >= J.n_mb) return;
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(J.mbs + mb));
+    if (d.x & 3u) return;  // intra MB: k_intra's job
+    const int n_parts = (int)((d.x >> 2) & 127u), n_coef = (int)((d.x >> 9) & 511u);
+    const uint32_t blkmask = (d.x >> 18) & 63u;
+    const int S = g.S;
+    const int mbx = (int)(mb % (uint32_t)g.mbw), mby = (int)(mb / (uint32_t)g.mbw);
+    const size_t ysz = (size_t)S * g.H;
+    const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
+    const int lrow = lane >> 1, lhalf = lane & 1;
+    const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1;
+    const int ypix = yoff + lrow * S + lhalf * 8;                              // this lane's luma pixels
+    const int cpix = coff + (cpl ? (S >> 1) : 0) + crow * S + chalf * 4;       // this lane's chroma pixels
+    const mobi_part* parts = J.parts + d.y;
+    uint32_t y0, y1, c0;
+
+    if (n_parts == 1) {
+        const PartV p = ld_part(parts);
+        const uint8_t* ref = J.ref[p.ref - 1];
+        mc_row8(ref + ypix + (p.mvy >> 1) * S + (p.mvx >> 1), S, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
+        const int cx = p.mvx >> 1, cy = p.mvy >> 1;
+        c0 = mc_row4(ref + ysz + cpix + (cy >> 1) * S + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1));
+    } else {
+        // partition map at 2x2-pixel granularity (leaves go down to 2x2, MD:1726)
+        uint8_t* map = s_map[warp];
+        for (int i = lane; i < n_parts; i += 32) {
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(parts + i));
+            const int x2 = w.x & 15, y2 = (w.x >> 4) & 15, cw = 1 << ((w.x >> 8) & 3), ch = 1 << ((w.x >> 10) & 3);
+            for (int yy = 0; yy < ch; yy++) for (int xx = 0; xx < cw; xx++) map[(y2 + yy) * 8 + x2 + xx] = (uint8_t)i;
+        }
+        __syncwarp();
+        const uint32_t ml = *reinterpret_cast<const uint32_t*>(map + (lrow >> 1) * 8 + lhalf * 4);
+        if (ml == (ml & 255u) * 0x01010101u) {
+            const PartV p = ld_part(parts + (ml & 255u));
+            mc_row8(J.ref[p.ref - 1] + ypix + (p.mvy >> 1) * S + (p.mvx >> 1), S, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
+        } else {
+            uint32_t o[2] = {0, 0};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const PartV p = ld_part(parts + ((ml >> (8 * c)) & 255u));
+                const uint8_t* s = J.ref[p.ref - 1] + ypix + 2 * c + (p.mvy >> 1) * S + (p.mvx >> 1);
+                const int ph = (p.mvx & 1) | ((p.mvy & 1) << 1);
+                const uint32_t v = mc_px(s, S, ph) | mc_px(s + 1, S, ph) << 8;
+                o[c >> 1] |= v << (16 * (c & 1));
+            }
+            y0 = o[0]; y1 = o[1];
+        }
+        const uint32_t mc = *reinterpret_cast<const uint32_t*>(map + crow * 8 + chalf * 4);
+        if (mc == (mc & 255u) * 0x01010101u) {
+            const PartV p = ld_part(parts + (mc & 255u));
+            const int cx = p.mvx >> 1, cy = p.mvy >> 1;
+            c0 = mc_row4(J.ref[p.ref - 1] + ysz + cpix + (cy >> 1) * S + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1));
+        } else {
+            c0 = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const PartV p = ld_part(parts + ((mc >> (8 * c)) & 255u));
+                const int cx = p.mvx >> 1, cy = p.mvy >> 1;
+                c0 |= mc_px(J.ref[p.ref - 1] + ysz + cpix + c + (cy >> 1) * S + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1)) << (8 * c);
+            }
+        }
+    }
+
+    if (n_coef) {
+        int32_t* cb = s_coef[warp];
+        for (int i = lane; i < 96; i += 32) reinterpret_cast<int4*>(cb)[i] = make_int4(0, 0, 0, 0);
+        __syncwarp();
+        uint32_t m8 = 0;
+        const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs + d.z);
+        for (int j = lane; j < n_coef; j += 32) {
+            const uint32_t c = __ldg(cf + j);
+            const int level = (int)(int16_t)(c & 0xFFFFu);
+            const uint32_t pos = (c >> 16) & 63u, sub = (c >> 22) & 3u, blk = (c >> 24) & 7u, is8 = c >> 31;
+            const uint32_t w = s_qtab[is8 ? pos : 64u + pos];
+            const int val = (int)(w >> 8) * level;  // MD:3427-3429
+            cb[blk * 64u + (is8 ? (w & 63u) : sub * 16u + (w & 15u))] = val;
+            m8 |= is8 << blk;
+        }
+        m8 = __reduce_or_sync(0xffffffffu, m8);
+        __syncwarp();
+
+        int32_t in[8], v[8];
+        // ---- luma: lane (block lb, row r) ----
+        if (blkmask & 15u) {
+            const int lb = ((lane >> 4) << 1) | (lane & 1), r = (lane >> 1) & 7, i4 = r & 3, s0 = (r >> 2) * 2;
+            const bool has = (blkmask >> lb) & 1u, is8 = (m8 >> lb) & 1u;
+            int32_t* B = cb + lb * 64;
+            if (has) {
+                if (is8) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) in[k] = B[8 * r + k];
+                    if (r == 0) in[0] += 32;
+                    bfly8(in, v);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { in[k] = B[s0 * 16 + 4 * i4 + k]; in[4 + k] = B[(s0 + 1) * 16 + 4 * i4 + k]; }
+                    if (i4 == 0) { in[0] += 32; in[4] += 32; }
+                    bfly4(in, v); bfly4(in + 4, v + 4);
+                }
+            }
+            __syncwarp();
+            if (has) {
+                if (is8) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) B[8 * k + r] = v[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { B[s0 * 16 + 4 * k + i4] = v[k]; B[(s0 + 1) * 16 + 4 * k + i4] = v[4 + k]; }
+                }
+            }
+            __syncwarp();
+            if (has) {
+                if (is8) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) in[k] = B[8 * r + k];
+                    bfly8(in, v);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { in[k] = B[s0 * 16 + 4 * i4 + k]; in[4 + k] = B[(s0 + 1) * 16 + 4 * i4 + k]; }
+                    bfly4(in, v); bfly4(in + 4, v + 4);
+                }
+                y0 = addclip4(y0, v); y1 = addclip4(y1, v + 4);
+            }
+        }
+        // ---- chroma: lane (plane cpl, row crow, half chalf); the 8-point passes are computed by both halves ----
+        if (blkmask & 48u) {
+            const int cbk = 4 + cpl, r = crow, i4 = r & 3, s = (r >> 2) * 2 + chalf;
+            const bool has = (blkmask >> cbk) & 1u, is8 = (m8 >> cbk) & 1u;
+            int32_t* B = cb + cbk * 64;
+            if (has) {
+                if (is8) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) in[k] = B[8 * r + k];
+                    if (r == 0) in[0] += 32;
+                    bfly8(in, v);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) in[k] = B[s * 16 + 4 * i4 + k];
+                    if (i4 == 0) in[0] += 32;
+                    bfly4(in, v);
+                }
+            }
+            __syncwarp();
+            if (has) {
+                if (is8) {
+                    if (chalf == 0) {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) B[8 * k + r] = v[k];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) B[s * 16 + 4 * k + i4] = v[k];
+                }
+            }
+            __syncwarp();
+            if (has) {
+                if (is8) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) in[k] = B[8 * r + k];
+                    bfly8(in, v);
+                    c0 = addclip4(c0, chalf ? v + 4 : v);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) in[k] = B[s * 16 + 4 * i4 + k];
+                    bfly4(in, v);
+                    c0 = addclip4(c0, v);
+                }
+            }
+        }
+    }
+
+    *reinterpret_cast<uint2*>(J.dst + ypix) = make_uint2(y0, y1);
+    *reinterpret_cast<uint32_t*>(J.dst + ysz + cpix) = c0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// intra macroblocks
+// ------------------------------------------------------------------------------------------------
+// Shared tiles: luma rows y-1..y+15, columns x-4..x+27 (column x at index 4, so x-1 = 3 and the
+// top-right / right-hand run x+16..x+20 = 20..24); chroma rows c-1..c+7, column c at index 4.
+struct IntraSmem {
+    uint8_t y[17][32];
+    uint8_t c[2][9][16];
+    int32_t coef[64];
+};
+
+__device__ __forceinline__ uint32_t nb_luma(const DevJob& J, const Geom& g, int flat, uint32_t m) {
+    if (flat < 0 || flat >= g.S * g.H) return 0;
+    const int row = flat >> g.log2S, col = flat & (g.S - 1);
+    if (col >= g.W) return 0;                                       // stride padding: never written
+    if ((uint32_t)((row >> 4) * g.mbw + (col >> 4)) >= m) return 0; // later in decode order: still zero in the reference
+    return __ldcg(J.dst + flat);
+}
+__device__ __forceinline__ uint32_t nb_chroma(const DevJob& J, const Geom& g, int flat, uint32_t m) {
+    if (flat < 0 || flat >= (g.S * g.H >> 1)) return 0;
+    const int row = flat >> g.log2S, col = flat & (g.S - 1);
+    const int pc = col < (g.S >> 1) ? col : col - (g.S >> 1);
+    if (pc >= (g.W >> 1)) return 0;
+    if ((uint32_t)((row >> 3) * g.mbw + (pc >> 3)) >= m) return 0;
+    return __ldcg(J.dst + (size_t)g.S * g.H + flat);
+}
+
+// Value of pixel (x,y) of an NxN block under predictor `mode` (0,1,4..8: MD:1890-2472 / 2475-2769 closed forms).
+// t points at the block's top-left pixel inside a shared tile with row pitch ts.
+__device__ __forceinline__ int dir_px(const uint8_t* t, int ts, int mode, int N, int x, int y) {
+#define TT(k) ((int)t[-ts + (k)])
+#define LL(k) ((int)t[(k) * ts - 1])
+    switch (mode) {
+    case 0: return TT(x);
+    case 1: return LL(y);
+    case 4: {
+        const int z = x + 2 * y, k = y + (x >> 1);
+        if (z > 2 * N - 3) return LL(N - 1);
+        if (z == 2 * N - 3) return (LL(N - 2) + 3 * LL(N - 1) + 2) >> 2;
+        if (z & 1) return (LL(k) + 2 * LL(k + 1) + LL(k + 2) + 2) >> 2;
+        return (LL(k) + LL(k + 1) + 1) >> 1; }
+    case 5: {
+        const int z = 2 * y - x, k = y - (x >> 1);
+        if (z < -1) return (TT(x - 2 * y - 1) + 2 * TT(x - 2 * y - 2) + TT(x - 2 * y - 3) + 2) >> 2;
+        if (z == -1) return (LL(0) + 2 * TT(-1) + TT(0) + 2) >> 2;
+        if (z & 1) return (LL(k - 2) + 2 * LL(k - 1) + LL(k) + 2) >> 2;   // LL(-1) == TT(-1) == top-left
+        return (LL(k - 1) + LL(k) + 1) >> 1; }
+    case 6: {
+        const int z = 2 * x - y, k = x - (y >> 1);
+        if (z < -1) return (LL(y - 2 * x - 1) + 2 * LL(y - 2 * x - 2) + LL(y - 2 * x - 3) + 2) >> 2;
+        if (z == -1) return (LL(0) + 2 * TT(-1) + TT(0) + 2) >> 2;
+        if (z & 1) return (TT(k - 2) + 2 * TT(k - 1) + TT(k) + 2) >> 2;
+        return (TT(k - 1) + TT(k) + 1) >> 1; }
+    case 7:
+        if (x > y) return (TT(x - y - 2) + 2 * TT(x - y - 1) + TT(x - y) + 2) >> 2;
+        if (x < y) return (LL(y - x - 2) + 2 * LL(y - x - 1) + LL(y - x) + 2) >> 2;
+        return (TT(0) + 2 * TT(-1) + LL(0) + 2) >> 2;
+    case 8: {
+        const int k = x + (y >> 1);
+        if (y & 1) return (TT(k) + 2 * TT(k + 1) + TT(k + 2) + 2) >> 2;
+        return (TT(k) + TT(k + 1) + 1) >> 1; }
+    }
+    return 0;
+#undef TT
+#undef LL
+}
+// Unclipped plane-predictor value (sub_1167BC MD:3017 for N=16, sub_116CCC MD:3168 for 8, sub_117E98 MD:3253 for 4),
+// the reference's running sums written in closed form (all arithmetic int32, wrap-around like C#).
+__device__ __forceinline__ int plane_val(const uint8_t* t, int ts, int N, int delta, int x, int y) {
+    const int l = t[(N - 1) * ts - 1], tt = t[-ts + N - 1], T = t[-ts + x], L = t[y * ts - 1];
+    const int m = ((l + tt + 1) >> 1) + delta * 2;
+    if (N == 16) {
+        const int gx = (m - l + 1) >> 1, gy = (m - tt + 1) >> 1;
+        const int Bc = (l * 8 + (x + 1) * gx) - T * 8 + 1, A = T * 64 + (y + 1) * (Bc >> 1);
+        const int step = (tt * 8 + (y + 1) * gy) - L * 8 + 1, run = L * 64 + (x + 1) * (step >> 1);
+        return (A + run + 64) >> 7;
+    }
+    const int sh = N == 8 ? 3 : 2;
+    const int gx = m - l, gy = m - tt;
+    const int Bc = ((l << sh) + (x + 1) * gx) - (T << sh), A = (T << (2 * sh)) + (y + 1) * Bc;
+    const int step = ((tt << sh) + (y + 1) * gy) - (L << sh), run = (L << (2 * sh)) + (x + 1) * step;
+    return N == 8 ? (A + run + 64) >> 7 : (A + run + 16) >> 5;
+}
+// The reference ORs four unclipped values into one u32 (MD:3064-3074): byte k also receives the
+// overflow of bytes < k of the same word.
+__device__ __forceinline__ uint8_t plane_px(const uint8_t* t, int ts, int N, int delta, int x, int y) {
+    uint32_t acc = 0;
+    for (int xx = x & ~3; xx <= x; xx++) acc |= (uint32_t)plane_val(t, ts, N, delta, xx, y) >> (8 * (x - xx));
+    return (uint8_t)acc;
+}
+
+// One intra op: predict an NxN block inside a shared tile (t = its top-left pixel).
+__device__ void intra_predict(uint8_t* t, int ts, int mode, int N, int delta, bool left_av, bool top_av, int lane) {
+    const int npx = N * N;
+    uint8_t out[8];
+    int cnt = 0;
+    if (mode == 3) {  // DC by flat-offset availability (MD:1920-2022, 2501-2580)
+        int sum = 0;
+        if (top_av) for (int k = 0; k < N; k++) sum += t[-ts + k];
+        if (left_av) for (int k = 0; k < N; k++) sum += t[k * ts - 1];
+        int dc;
+        if (top_av && left_av) dc = (sum + N) / (2 * N);
+        else if (top_av || left_av) dc = (sum + N / 2) / N;
+        else dc = 0x80;
+        for (int i = lane; i < npx; i += 32) out[cnt++] = (uint8_t)dc;
+    } else if (mode == 2) {
+        for (int i = lane; i < npx; i += 32) out[cnt++] = plane_px(t, ts, N, delta, i % N, i / N);
+    } else {
+        for (int i = lane; i < npx; i += 32) out[cnt++] = (uint8_t)dir_px(t, ts, mode, N, i % N, i / N);
+    }
+    __syncwarp();
+    cnt = 0;
+    for (int i = lane; i < npx; i += 32) t[(i / N) * ts + (i % N)] = out[cnt++];
+    __syncwarp();
+}
+
+// Residual of one transform unit added onto the tile (loc_116540 MD:2931 / sub_1166E8 MD:2958).
+__device__ void intra_residual(uint8_t* t, int ts, int N, int32_t* cb, const uint32_t* __restrict__ qtab,
+                               const uint32_t* __restrict__ coefs, uint32_t& cursor, uint32_t end, int lane) {
+    for (int i = lane; i < N * N; i += 32) cb[i] = 0;
+    __syncwarp();
+    for (;;) {  // the unit's coefficients end at the record flagged "last"
+        const uint32_t j = cursor + lane;
+        const uint32_t c = j < end ? __ldg(coefs + j) : 0u;
+        const uint32_t lastmask = __ballot_sync(0xffffffffu, j < end && ((c >> 30) & 1u));
+        const int n = lastmask ? __ffs(lastmask) : 32;
+        if (lane < n && j < end) {
+            const uint32_t pos = (c >> 16) & 63u;
+            const uint32_t w = __ldg(qtab + (N == 8 ? pos : 64u + pos));
+            cb[w & (uint32_t)(N * N - 1)] = (int)(w >> 8) * (int)(int16_t)(c & 0xFFFFu);
+        }
+        cursor += n;
+        if (lastmask || cursor >= end) break;
+    }
+    __syncwarp();
+    int32_t in[8], v[8];
+    if (lane < N) {
+        for (int k = 0; k < N; k++) in[k] = cb[N * lane + k];
+        if (lane == 0) in[0] += 32;
+        if (N == 8) bfly8(in, v); else bfly4(in, v);
+    }
+    __syncwarp();
+    if (lane < N) for (int k = 0; k < N; k++) cb[N * k + lane] = v[k];
+    __syncwarp();
+    if (lane < N) {
+        for (int k = 0; k < N; k++) in[k] = cb[N * lane + k];
+        if (N == 8) bfly8(in, v); else bfly4(in, v);
+        for (int k = 0; k < N; k++) t[lane * ts + k] = (uint8_t)clip255((int)t[lane * ts + k] + (v[k] >> 6));
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(INTRA_WARPS * 32) k_intra(const DevJob* __restrict__ jobs, const IntraWork* __restrict__ work, uint32_t n_work,
+                                                           uint32_t* ticket, uint32_t ticket_base, uint32_t stamp, Geom g) {
+    __shared__ __align__(16) IntraSmem s_all[INTRA_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    IntraSmem& sm = s_all[warp];
+    const int S = g.S;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u) - ticket_base;
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_work) break;
+        const IntraWork wk = work[t];
+        const DevJob& J = jobs[wk.job];
+        const uint32_t m = __ldg(J.intra + wk.rank);
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(J.mbs + m));
+        const int n_ops = (int)((d.x >> 2) & 127u);
+        const uint32_t coef_end = d.z + ((d.x >> 9) & 511u);
+        uint32_t cursor = d.z;
+        const int mbx = (int)(m % (uint32_t)g.mbw), mby = (int)(m / (uint32_t)g.mbw);
+        const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
+
+        // wait for the intra neighbours this MB may read: left, top-left, top, top-right in raster
+        // numbering (which also covers the flat-address wrap at the picture edges when W == Stride)
+        if (lane < 4) {
+            const int nb = lane == 0 ? (int)m - 1 : (int)m - g.mbw - 2 + lane;
+            if (nb >= 0 && nb < (int)m && (__ldg(&J.mbs[nb].info) & 3u) == 1u) {
+                volatile uint32_t* f = J.flags + nb;
+                while (*f != stamp) __nanosleep(32);
+            }
+        }
+        __syncwarp();
+        __threadfence();
+
+        // stage neighbourhoods; the MB's own pixels start at zero like the reference's fresh planes
+        for (int r = 0; r < 17; r++) {
+            const int c = lane;
+            uint32_t v = 0;
+            if ((r == 0 && c >= 3 && c <= 24) || (r > 0 && (c == 3 || (c >= 20 && c <= 24))))
+                v = nb_luma(J, g, yoff + (r - 1) * S + (c - 4), m);
+            sm.y[r][c] = (uint8_t)v;
+        }
+        for (int i = lane; i < 2 * 9 * 16; i += 32) {
+            const int p = i / 144, r = (i % 144) / 16, c = i % 16;
+            uint32_t v = 0;
+            if ((r == 0 && c >= 3 && c <= 11) || (r > 0 && c == 3))
+                v = nb_chroma(J, g, coff + (p ? (S >> 1) : 0) + (r - 1) * S + (c - 4), m);
+            sm.c[p][r][c] = (uint8_t)v;
+        }
+        __syncwarp();
+
+        const uint32_t* qtab = J.hdr->qtab;
+        const uint32_t* coefs = reinterpret_cast<const uint32_t*>(J.coefs);
+        for (int k = 0; k < n_ops; k++) {
+            const uint32_t op = __ldg(J.ops + d.y + k);
+            const int mode = (int)(op & 31u), plane = (int)((op >> 6) & 3u), x4 = (int)((op >> 8) & 3u), y4 = (int)((op >> 10) & 3u);
+            const bool res = (op >> 5) & 1u;
+            const int delta = (int)(int16_t)(op >> 16);
+            uint8_t* tp; int ts, off;
+            if (plane == 0) { ts = 32; tp = &sm.y[1 + y4 * 4][4 + x4 * 4]; off = yoff + y4 * 4 * S + x4 * 4; }
+            else { ts = 16; tp = &sm.c[plane - 1][1 + y4 * 4][4 + x4 * 4]; off = coff + (plane == 2 ? (S >> 1) : 0) + y4 * 4 * S + x4 * 4; }
+            int N, pm = mode;
+            if (mode == 20) { N = 16; pm = 2; } else if (mode >= 10) { N = 4; pm = mode - 10; } else N = 8;
+            if (pm != 9) {
+                const bool left_av = ((off - (plane == 2 ? (S >> 1) : 0)) & (S - 1)) != 0;  // MD:1923, VOffsetfix MD:1885
+                const bool top_av = off >= S;                                               // MD:1924
+                intra_predict(tp, ts, pm, N, delta, left_av, top_av, lane);
+            }
+            if (res) intra_residual(tp, ts, N == 16 ? 8 : N, sm.coef, qtab, coefs, cursor, coef_end, lane);
+        }
+
+        // write the macroblock out
+        {
+            const int lrow = lane >> 1, lhalf = lane & 1;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.y[1 + lrow][4 + lhalf * 8]);
+            *reinterpret_cast<uint2*>(J.dst + yoff + lrow * S + lhalf * 8) = make_uint2(src[0], src[1]);
+            const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1;
+            const uint32_t cv = *reinterpret_cast<const uint32_t*>(&sm.c[cpl][1 + crow][4 + chalf * 4]);
+            *reinterpret_cast<uint32_t*>(J.dst + (size_t)S * g.H + coff + (cpl ? (S >> 1) : 0) + crow * S + chalf * 4) = cv;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *(volatile uint32_t*)(J.flags + m) = stamp;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// YUV -> BGRA (MD:260-323): strict binary32, source order, no contraction (file is built with -fmad=false)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bgra(const uint8_t* const* __restrict__ srcs, uint8_t* __restrict__ dst, int pitch, size_t per, Geom g) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= g.W) return;
+    const uint8_t* __restrict__ src = srcs[blockIdx.z];
+    dst += per * blockIdx.z;
+    const int S = g.S;
+    const uint8_t* Y = src;
+    const uint8_t* C = src + (size_t)S * g.H;
+    const float Y2 = (float)Y[y * S + x];
+    const int ci = (y >> 1) * S + (x >> 1), h = S >> 1;
+    float U = (float)C[ci] - 128.0f, V = (float)C[ci + h] - 128.0f;
+    if (x != g.W - 1 && y != g.H - 1) {
+        switch ((x & 1) | ((y & 1) << 1)) {
+        case 1: U += (float)C[ci + 1] - 128.0f; V += (float)C[ci + 1 + h] - 128.0f; U /= 2.0f; V /= 2.0f; break;
+        case 2: U += (float)C[ci + S] - 128.0f; V += (float)C[ci + S + h] - 128.0f; U /= 2.0f; V /= 2.0f; break;
+        case 3:
+            U += (float)C[ci + 1] - 128.0f; V += (float)C[ci + 1 + h] - 128.0f;
+            U += (float)C[ci + S] - 128.0f; V += (float)C[ci + S + h] - 128.0f;
+            U += (float)C[ci + 1 + S] - 128.0f; V += (float)C[ci + 1 + S + h] - 128.0f;
+            U /= 4.0f; V /= 4.0f; break;
+        }
+    }
+    float R, G, B;
+    if (g.version == MOBI_MOFLEX3DS) {
+        R = Y2 + 1.420f * V; G = Y2 - 0.344f * U - 0.714f * V; B = Y2 + 1.772f * U;
+        R = __fdiv_rn((R - 16.0f) * 255.0f, 255.0f - 16.0f);
+        G = __fdiv_rn((G - 16.0f) * 255.0f, 255.0f - 16.0f);
+        B = __fdiv_rn((B - 16.0f) * 255.0f, 255.0f - 16.0f);
+    } else {
+        R = (float)((int)Y2 + (int)U - (int)V); G = (float)((int)Y2 + (int)V); B = (float)((int)Y2 - (int)U - (int)V);
+    }
+    R = R < 0.0f ? 0.0f : (R > 255.0f ? 255.0f : R);
+    G = G < 0.0f ? 0.0f : (G > 255.0f ? 255.0f : G);
+    B = B < 0.0f ? 0.0f : (B > 255.0f ? 255.0f : B);
+    const uint32_t px = (uint32_t)(int)B | (uint32_t)(int)G << 8 | (uint32_t)(int)R << 16 | 0xFF000000u;
+    *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + (size_t)x * 4) = px;
+}
+
+// strided planes -> tight I420, 4 bytes per thread
+__global__ void __launch_bounds__(256) k_pack_i420(const uint8_t* const* __restrict__ srcs, uint8_t* __restrict__ dst, Geom g) {
+    const uint8_t* src = srcs[blockIdx.y];
+    const int W = g.W, H = g.H, S = g.S;
+    const int ywords = W * H / 4, cwords = W * H / 16;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ywords + 2 * cwords) return;
+    uint8_t* out = dst + (size_t)blockIdx.y * (size_t)(W * H * 3 / 2);
+    uint32_t v;
+    if (i < ywords) {
+        const int b = i * 4, y = b / W, x = b % W;
+        v = *reinterpret_cast<const uint32_t*>(src + y * S + x);
+    } else {
+        const int j = i - ywords, p = j >= cwords, b = (j - p * cwords) * 4, y = b / (W / 2), x = b % (W / 2);
+        v = *reinterpret_cast<const uint32_t*>(src + (size_t)S * H + y * S + x + p * (S / 2));
+    }
+    reinterpret_cast<uint32_t*>(out)[i] = v;
+}
+
+}  // namespace
+
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, cudaStream_t st) {
+    if (n_jobs <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((g.mbw * g.mbh + INTER_WARPS - 1) / INTER_WARPS), (unsigned)n_jobs);
+    k_inter<<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_work, uint32_t* ticket, uint32_t ticket_base,
+                         uint32_t stamp, Geom g, int sm_count, cudaStream_t st, uint32_t* warps_launched) {
+    *warps_launched = 0;
+    if (n_work == 0) return cudaSuccess;
+    // every warp that holds a ticket must be resident: size the grid to what fits, never more
+    unsigned blocks = (unsigned)((n_work + INTRA_WARPS - 1) / INTRA_WARPS);
+    unsigned cap = (unsigned)sm_count * 8u;
+    if (blocks > cap) blocks = cap;
+    k_intra<<<blocks, INTRA_WARPS * 32, 0, st>>>(jobs, work, n_work, ticket, ticket_base, stamp, g);
+    *warps_launched = blocks * INTRA_WARPS;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bgra(const uint8_t* const* srcs, int n, uint8_t* dst, int dst_pitch, size_t dst_picture_bytes, Geom g, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((g.W + 255) / 256), (unsigned)g.H, (unsigned)n);
+    k_bgra<<<grid, 256, 0, st>>>(srcs, dst, dst_pitch, dst_picture_bytes, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_i420(const uint8_t* const* srcs, int n, uint8_t* dst, Geom g, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const int words = g.W * g.H * 3 / 8;
+    dim3 grid((unsigned)((words + 255) / 256), (unsigned)n);
+    k_pack_i420<<<grid, 256, 0, st>>>(srcs, dst, g);
+    return cudaGetLastError();
+}
+
+}  // namespace mobi

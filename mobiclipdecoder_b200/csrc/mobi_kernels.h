@@ -1,0 +1,44 @@
+// Device-side job table and kernel launchers (implemented in mobi_kernels.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/mobicuda.h"
+
+namespace mobi {
+
+// One (stream, frame) unit of work inside a lock-step batch.  All pointers are device addresses.
+struct alignas(16) DevJob {
+    const mobi_frame_hdr* hdr;
+    const mobi_mb* mbs;
+    const mobi_part* parts;
+    const mobi_op* ops;
+    const mobi_coef* coefs;
+    const uint32_t* intra;   // raster indices of the frame's intra MBs
+    uint8_t* dst;            // luma plane of the picture being written (Stride*H), chroma follows at +Stride*H
+    const uint8_t* ref[5];   // ref[k-1]: luma plane of ring picture k (Y[k], MD:413); null when absent
+    uint32_t* flags;         // per-MB completion stamps of this stream (intra wavefront)
+    uint32_t n_mb, n_intra;
+    uint32_t pad[2];
+};
+
+struct IntraWork { uint32_t job, rank; };
+
+struct Geom {
+    int W, H, S, log2S, mbw, mbh, version;
+};
+
+// Inter macroblocks of every job: MC from the ring + dequant/IDCT/add/clip.  One warp per MB.
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, cudaStream_t st);
+// Intra macroblocks (I-frames and intra MBs of P-frames) in decode-order wavefront.  One warp per MB,
+// work handed out through an atomic ticket so that a waiting warp's dependencies are always running.
+// *warps_launched receives the number of warps started: each draws exactly one ticket past n_work, so the
+// next launch's ticket_base is ticket_base + n_work + *warps_launched.
+cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_work, uint32_t* ticket, uint32_t ticket_base,
+                         uint32_t stamp, Geom g, int sm_count, cudaStream_t st, uint32_t* warps_launched);
+// Y/UV planes of n pictures -> BGRA (MD:260-323). srcs = device array of luma plane pointers; picture i goes to
+// dst + i*dst_picture_bytes with dst_pitch bytes per row.
+cudaError_t launch_bgra(const uint8_t* const* srcs, int n, uint8_t* dst, int dst_pitch, size_t dst_picture_bytes, Geom g, cudaStream_t st);
+// Strided planes of n pictures -> tight I420 (n * W*H*3/2 bytes). srcs = device array of luma plane pointers.
+cudaError_t launch_pack_i420(const uint8_t* const* srcs, int n, uint8_t* dst, Geom g, cudaStream_t st);
+
+}  // namespace mobi

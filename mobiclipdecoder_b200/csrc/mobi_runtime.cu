@@ -1,0 +1,699 @@
+// libmobicuda.so runtime: the C ABI of include/mobicuda.h over the host parser (mobi_parse.cpp) and the
+// sm_100a kernels (mobi_kernels.cu).  "MD:n" = LibMobiclip/Codec/Mobiclip/MobiclipDecoder.cs:n.
+//
+// Memory plan (per GPU):
+//   ring      N streams x 6 pictures x (Stride*H luma + Stride*H/2 chroma + pad), zeroed once.  The kernels
+//             only ever write pixels inside the visible W x H area, so the stride padding stays zero for the
+//             life of the batch exactly as in the reference's freshly allocated planes (MD:107-108).
+//   flags     N x n_MB completion stamps for the intra wavefront (stamp = launch serial, never cleared).
+//   arena     one pinned host + one device buffer per in-flight step holding
+//             [DevJob table | IntraWork list | per stream: hdr, mbs, parts, ops, coefs, intra list],
+//             uploaded with a single cudaMemcpyAsync.  Two arenas alternate so that the host parses step
+//             k+1 while the GPU reconstructs step k.
+//   staged    device-resident copies of whole steps for the kernel-only replay (bench "value" leg, ncu).
+#include <cuda_runtime.h>
+#include <atomic>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include "mobi_kernels.h"
+#include "mobi_parse.h"
+
+namespace mobi {
+namespace {
+
+constexpr int RING = 6;  // Y[0..5] (MD:19)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- tiny persistent thread pool: parallel_for over stream indices --------------------------------
+class Pool {
+public:
+    explicit Pool(int n) {
+        for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void run(int n, const std::function<void(int)>& fn) {
+        if (th_.empty() || n <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+        {
+            std::lock_guard<std::mutex> l(m_);
+            fn_ = &fn; n_ = n; next_.store(0); active_ = (int)th_.size(); gen_++;
+        }
+        cv_.notify_all();
+        work();  // the caller helps
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return active_ == 0; });
+        fn_ = nullptr;
+    }
+    int size() const { return (int)th_.size(); }
+private:
+    void work() {
+        for (;;) {
+            int i = next_.fetch_add(1);
+            if (i >= n_) break;
+            (*fn_)(i);
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> l(m_);
+                if (--active_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_ = 0, active_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+struct Arena {
+    uint8_t* h = nullptr;  // pinned
+    uint8_t* d = nullptr;
+    size_t cap = 0;
+    cudaEvent_t consumed = nullptr;  // recorded after the kernels that read d
+    bool pending = false;
+};
+
+// Where one step's arrays live on the device, plus the host-side facts needed to launch it again.
+struct StepLayout {
+    size_t bytes = 0;
+    size_t jobs_off = 0, work_off = 0;
+    int n_jobs = 0, n_inter_jobs = 0;
+    uint32_t n_work = 0;
+    std::vector<int> job_stream;  // stream index of each job
+    uint64_t mbs = 0, inter_mbs = 0, intra_mbs = 0, parts = 0, coefs = 0, ops = 0;
+};
+
+struct Staged {
+    uint8_t* d = nullptr;
+    StepLayout L;
+};
+
+}  // namespace
+
+class Batch {
+public:
+    Batch(uint32_t w, uint32_t h, int version, int device, int n_streams, int n_threads)
+        : W_(w), H_(h), ver_(version), dev_(device), N_(n_streams), pool_(n_threads > 1 ? n_threads - 1 : 0) {
+        g_.W = (int)w; g_.H = (int)h; g_.S = stride_for(w); g_.version = version;
+        g_.log2S = g_.S == 256 ? 8 : g_.S == 512 ? 9 : 10;
+        g_.mbw = (int)w / 16; g_.mbh = (int)h / 16;
+        n_mb_ = (uint32_t)(g_.mbw * g_.mbh);
+        ysz_ = (size_t)g_.S * h;
+        pic_ = align_up(ysz_ * 3 / 2 + 256, 256);
+        for (int i = 0; i < n_streams; i++) parsers_.emplace_back(new Parser(w, h, version));
+        frames_.resize(n_streams);
+        count_.assign(n_streams, 0);
+        staged_count_.assign(n_streams, 0);
+    }
+    ~Batch() {
+        if (stream_) {
+            cudaSetDevice(dev_);
+            cudaStreamSynchronize(stream_);
+            clear_staged();
+            for (auto& a : arena_) { if (a.h) cudaFreeHost(a.h); if (a.d) cudaFree(a.d); if (a.consumed) cudaEventDestroy(a.consumed); }
+            if (ring_) cudaFree(ring_);
+            if (flags_) cudaFree(flags_);
+            if (ticket_) cudaFree(ticket_);
+            if (out_d_) cudaFree(out_d_);
+            if (out_h_) cudaFreeHost(out_h_);
+            if (ptr_d_) cudaFree(ptr_d_);
+            if (ptr_h_) cudaFreeHost(ptr_h_);
+            cudaStreamDestroy(stream_);
+        }
+    }
+
+    int init() {
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        cudaDeviceProp prop;
+        if (!ok(cudaGetDeviceProperties(&prop, dev_), "cudaGetDeviceProperties")) return MOBI_ERR_CUDA;
+        sm_count_ = prop.multiProcessorCount;
+        if (!ok(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return MOBI_ERR_CUDA;
+        if (!ok(cudaMalloc(&ring_, pic_ * RING * (size_t)N_), "cudaMalloc(ring)")) return MOBI_ERR_NOMEM;
+        if (!ok(cudaMemsetAsync(ring_, 0, pic_ * RING * (size_t)N_, stream_), "memset(ring)")) return MOBI_ERR_CUDA;
+        if (!ok(cudaMalloc(&flags_, sizeof(uint32_t) * n_mb_ * (size_t)N_), "cudaMalloc(flags)")) return MOBI_ERR_NOMEM;
+        if (!ok(cudaMemsetAsync(flags_, 0, sizeof(uint32_t) * n_mb_ * (size_t)N_, stream_), "memset(flags)")) return MOBI_ERR_CUDA;
+        if (!ok(cudaMalloc(&ticket_, 256), "cudaMalloc(ticket)")) return MOBI_ERR_NOMEM;
+        if (!ok(cudaMemsetAsync(ticket_, 0, 256, stream_), "memset(ticket)")) return MOBI_ERR_CUDA;
+        for (auto& a : arena_)
+            if (!ok(cudaEventCreateWithFlags(&a.consumed, cudaEventDisableTiming), "cudaEventCreate")) return MOBI_ERR_CUDA;
+        if (!ok(cudaMalloc(&ptr_d_, sizeof(void*) * (size_t)N_), "cudaMalloc(ptrs)")) return MOBI_ERR_NOMEM;
+        if (!ok(cudaMallocHost(&ptr_h_, sizeof(void*) * (size_t)N_), "cudaMallocHost(ptrs)")) return MOBI_ERR_NOMEM;
+        if (!ok(cudaStreamSynchronize(stream_), "init sync")) return MOBI_ERR_CUDA;
+        return MOBI_OK;
+    }
+
+    // ---- one lock-step advance from raw frame bytes ---------------------------------------------
+    int decode(const uint8_t* const* data, const int* len, int* offset, int* status) {
+        if (!data || !len || !offset) return set_err(MOBI_ERR_ARG, "null argument");
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        rc_.assign(N_, MOBI_OK);
+        pool_.run(N_, [&](int i) { rc_[i] = parsers_[i]->parse(data[i], len[i], &offset[i], frames_[i]); });
+        views_.resize(N_);
+        int n_ok = 0, first_bad = -1;
+        for (int i = 0; i < N_; i++) {
+            if (status) status[i] = rc_[i];
+            if (rc_[i] == MOBI_OK) { views_[i] = frames_[i].view(); n_ok++; }
+            else { views_[i] = mobi_packed_frame{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; if (first_bad < 0) first_bad = i; }
+        }
+        if (first_bad >= 0) set_err(rc_[first_bad], "stream %d: %s", first_bad, parsers_[first_bad]->error().c_str());
+        if (n_ok == 0) return first_bad >= 0 ? rc_[first_bad] : MOBI_OK;
+        Arena& a = arena_[cur_arena_];
+        cur_arena_ ^= 1;
+        StepLayout L;
+        int rc = pack_step(a, L, count_);
+        if (rc != MOBI_OK) return rc;
+        if (!ok(cudaMemcpyAsync(a.d, a.h, L.bytes, cudaMemcpyHostToDevice, stream_), "H2D arena")) return MOBI_ERR_CUDA;
+        stats_.h2d_bytes += L.bytes;
+        rc = launch_step(a.d, L);
+        if (rc != MOBI_OK) return rc;
+        cudaEventRecord(a.consumed, stream_);
+        a.pending = true;
+        for (int s : L.job_stream) count_[s]++;
+        return (first_bad >= 0 && N_ == 1) ? rc_[first_bad] : MOBI_OK;
+    }
+
+    // Reconstruct stream 0's next picture from caller-provided packed arrays (mobi_submit_packed).
+    int submit(int stream, const mobi_packed_frame* f) {
+        if (!f || !f->hdr) return set_err(MOBI_ERR_ARG, "null packed frame");
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        int rc = validate(*f, count_[stream]);
+        if (rc != MOBI_OK) return rc;
+        views_.assign(N_, mobi_packed_frame{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
+        views_[stream] = *f;
+        Arena& a = arena_[cur_arena_];
+        cur_arena_ ^= 1;
+        StepLayout L;
+        rc = pack_step(a, L, count_);
+        if (rc != MOBI_OK) return rc;
+        if (!ok(cudaMemcpyAsync(a.d, a.h, L.bytes, cudaMemcpyHostToDevice, stream_), "H2D arena")) return MOBI_ERR_CUDA;
+        stats_.h2d_bytes += L.bytes;
+        rc = launch_step(a.d, L);
+        if (rc != MOBI_OK) return rc;
+        cudaEventRecord(a.consumed, stream_);
+        a.pending = true;
+        count_[stream]++;
+        quant_override_ = f->hdr->quantizer; yuv_override_ = f->hdr->yuv_format; have_override_ = true;
+        return MOBI_OK;
+    }
+
+    // ---- staging / replay -------------------------------------------------------------------------
+    int stage(const uint8_t* const* data, const int* len, int* offset) {
+        if (!data || !len || !offset) return set_err(MOBI_ERR_ARG, "null argument");
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        rc_.assign(N_, MOBI_OK);
+        pool_.run(N_, [&](int i) { rc_[i] = parsers_[i]->parse(data[i], len[i], &offset[i], frames_[i]); });
+        views_.resize(N_);
+        for (int i = 0; i < N_; i++) {
+            if (rc_[i] != MOBI_OK) return set_err(rc_[i], "stream %d: %s", i, parsers_[i]->error().c_str());
+            views_[i] = frames_[i].view();
+        }
+        Arena& a = arena_[cur_arena_];
+        cur_arena_ ^= 1;
+        Staged st;
+        int rc = pack_step(a, st.L, staged_count_);
+        if (rc != MOBI_OK) return rc;
+        if (!ok(cudaMalloc(&st.d, st.L.bytes), "cudaMalloc(staged step)")) return MOBI_ERR_NOMEM;
+        // the job table holds device addresses relative to the arena's device buffer: rebase onto st.d
+        rebase(a.h, st.L, a.d, st.d);
+        if (!ok(cudaMemcpyAsync(st.d, a.h, st.L.bytes, cudaMemcpyHostToDevice, stream_), "H2D staged")) return MOBI_ERR_CUDA;
+        cudaEventRecord(a.consumed, stream_);
+        a.pending = true;
+        for (int s : st.L.job_stream) staged_count_[s]++;
+        staged_.push_back(std::move(st));
+        return MOBI_OK;
+    }
+    int replay(int first, int count) {
+        if (first < 0 || count < 0 || first + count > (int)staged_.size()) return set_err(MOBI_ERR_ARG, "replay range outside staged steps");
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        for (int k = first; k < first + count; k++) {
+            int rc = launch_step(staged_[k].d, staged_[k].L);
+            if (rc != MOBI_OK) return rc;
+            for (int s : staged_[k].L.job_stream) count_[s]++;
+        }
+        return MOBI_OK;
+    }
+    int staged_steps() const { return (int)staged_.size(); }
+    void clear_staged() {
+        if (stream_) cudaStreamSynchronize(stream_);
+        for (auto& s : staged_) cudaFree(s.d);
+        staged_.clear();
+        std::fill(staged_count_.begin(), staged_count_.end(), 0);
+    }
+    // Ring back to "nothing decoded".  Staged steps stay valid: they were laid out from picture 0.
+    int reset(bool parsers_too) {
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        if (!ok(cudaStreamSynchronize(stream_), "sync")) return MOBI_ERR_CUDA;
+        std::fill(count_.begin(), count_.end(), 0);
+        if (parsers_too) { for (auto& p : parsers_) p->reset(); std::fill(staged_count_.begin(), staged_count_.end(), 0); }
+        have_override_ = false;
+        return MOBI_OK;
+    }
+    int sync() {
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        return ok(cudaStreamSynchronize(stream_), "cudaStreamSynchronize") ? MOBI_OK : MOBI_ERR_CUDA;
+    }
+
+    // ---- read-back --------------------------------------------------------------------------------
+    int read_strided(int s, uint8_t* y, uint8_t* uv) {
+        if (s < 0 || s >= N_) return set_err(MOBI_ERR_ARG, "stream index");
+        if (count_[s] == 0) return set_err(MOBI_ERR_STATE, "no picture decoded yet");
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        const uint8_t* p = picture(s, count_[s] - 1);
+        if (y && !ok(cudaMemcpyAsync(y, p, ysz_, cudaMemcpyDeviceToHost, stream_), "D2H luma")) return MOBI_ERR_CUDA;
+        if (uv && !ok(cudaMemcpyAsync(uv, p + ysz_, ysz_ / 2, cudaMemcpyDeviceToHost, stream_), "D2H chroma")) return MOBI_ERR_CUDA;
+        stats_.d2h_bytes += (y ? ysz_ : 0) + (uv ? ysz_ / 2 : 0);
+        return sync();
+    }
+    // tight I420 of every stream's newest picture; dst may be null (device-side pack only)
+    int read_yuv_all(uint8_t* dst) {
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        const size_t per = (size_t)W_ * H_ * 3 / 2, total = per * N_;
+        int rc = ensure_out(total);
+        if (rc != MOBI_OK) return rc;
+        for (int s = 0; s < N_; s++) {
+            if (count_[s] == 0) return set_err(MOBI_ERR_STATE, "stream %d: no picture decoded yet", s);
+            ptr_h_[s] = picture(s, count_[s] - 1);
+        }
+        // ptr_h_ is re-used every call: the previous call's copy has completed because every read syncs
+        if (!ok(cudaMemcpyAsync(ptr_d_, ptr_h_, sizeof(void*) * N_, cudaMemcpyHostToDevice, stream_), "H2D ptrs")) return MOBI_ERR_CUDA;
+        if (!ok(launch_pack_i420(ptr_d_, N_, out_d_, g_, stream_), "k_pack_i420")) return MOBI_ERR_CUDA;
+        stats_.launches++;
+        if (dst) {
+            if (!ok(cudaMemcpyAsync(out_h_, out_d_, total, cudaMemcpyDeviceToHost, stream_), "D2H i420")) return MOBI_ERR_CUDA;
+            stats_.d2h_bytes += total;
+        }
+        rc = sync();
+        if (rc != MOBI_OK) return rc;
+        if (dst) {
+            // pinned staging -> caller memory (pageable in general), fanned out over the pool
+            const int chunks = N_;
+            pool_.run(chunks, [&](int i) { std::memcpy(dst + per * i, out_h_ + per * i, per); });
+        }
+        return MOBI_OK;
+    }
+    int read_yuv_one(int s, uint8_t* y, uint8_t* u, uint8_t* v) {
+        if (s < 0 || s >= N_) return set_err(MOBI_ERR_ARG, "stream index");
+        if (count_[s] == 0) return set_err(MOBI_ERR_STATE, "no picture decoded yet");
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        const uint8_t* p = picture(s, count_[s] - 1);
+        const size_t S = (size_t)g_.S;
+        if (y && !ok(cudaMemcpy2DAsync(y, W_, p, S, W_, H_, cudaMemcpyDeviceToHost, stream_), "D2H Y")) return MOBI_ERR_CUDA;
+        if (u && !ok(cudaMemcpy2DAsync(u, W_ / 2, p + ysz_, S, W_ / 2, H_ / 2, cudaMemcpyDeviceToHost, stream_), "D2H U")) return MOBI_ERR_CUDA;
+        if (v && !ok(cudaMemcpy2DAsync(v, W_ / 2, p + ysz_ + S / 2, S, W_ / 2, H_ / 2, cudaMemcpyDeviceToHost, stream_), "D2H V")) return MOBI_ERR_CUDA;
+        stats_.d2h_bytes += (size_t)W_ * H_ * 3 / 2;
+        return sync();
+    }
+    // BGRA of every stream's newest picture into one device buffer; optionally down to the host.
+    int bgra_all(uint8_t* dst) {
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        const size_t per = (size_t)W_ * H_ * 4, total = per * N_;
+        int rc = ensure_out(total);
+        if (rc != MOBI_OK) return rc;
+        for (int s = 0; s < N_; s++) {
+            if (count_[s] == 0) return set_err(MOBI_ERR_STATE, "stream %d: no picture decoded yet", s);
+            ptr_h_[s] = picture(s, count_[s] - 1);
+        }
+        if (!ok(cudaMemcpyAsync(ptr_d_, ptr_h_, sizeof(void*) * N_, cudaMemcpyHostToDevice, stream_), "H2D ptrs")) return MOBI_ERR_CUDA;
+        if (!ok(launch_bgra(ptr_d_, N_, out_d_, (int)W_ * 4, per, g_, stream_), "k_bgra")) return MOBI_ERR_CUDA;
+        stats_.launches++;
+        if (dst) {
+            if (!ok(cudaMemcpyAsync(out_h_, out_d_, total, cudaMemcpyDeviceToHost, stream_), "D2H bgra")) return MOBI_ERR_CUDA;
+            stats_.d2h_bytes += total;
+        }
+        rc = sync();
+        if (rc != MOBI_OK) return rc;
+        if (dst) pool_.run(N_, [&](int i) { std::memcpy(dst + per * i, out_h_ + per * i, per); });
+        return MOBI_OK;
+    }
+    int read_bgra_one(int s, uint8_t* dst, int dst_stride) {
+        if (s < 0 || s >= N_ || !dst || dst_stride < (int)W_ * 4) return set_err(MOBI_ERR_ARG, "bad bgra destination");
+        if (count_[s] == 0) return set_err(MOBI_ERR_STATE, "no picture decoded yet");
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        const size_t per = (size_t)W_ * H_ * 4;
+        int rc = ensure_out(per);
+        if (rc != MOBI_OK) return rc;
+        ptr_h_[0] = picture(s, count_[s] - 1);
+        if (!ok(cudaMemcpyAsync(ptr_d_, ptr_h_, sizeof(void*), cudaMemcpyHostToDevice, stream_), "H2D ptrs")) return MOBI_ERR_CUDA;
+        if (!ok(launch_bgra(ptr_d_, 1, out_d_, (int)W_ * 4, per, g_, stream_), "k_bgra")) return MOBI_ERR_CUDA;
+        stats_.launches++;
+        if (!ok(cudaMemcpy2DAsync(dst, (size_t)dst_stride, out_d_, (size_t)W_ * 4, (size_t)W_ * 4, H_, cudaMemcpyDeviceToHost, stream_), "D2H bgra")) return MOBI_ERR_CUDA;
+        stats_.d2h_bytes += per;
+        return sync();
+    }
+
+    void get_state(int s, uint32_t* q, uint32_t* yf, int* stride) const {
+        if (q) *q = have_override_ ? quant_override_ : parsers_[s]->quantizer();
+        if (yf) *yf = have_override_ ? yuv_override_ : parsers_[s]->yuv_format();
+        if (stride) *stride = g_.S;
+    }
+    const char* error() const { return err_.c_str(); }
+    void* cuda_stream() const { return (void*)stream_; }
+    const mobi_batch_stats& stats() const { return stats_; }
+    void clear_stats() { std::memset(&stats_, 0, sizeof stats_); }
+    int n_streams() const { return N_; }
+    uint32_t width() const { return W_; }
+    uint32_t height() const { return H_; }
+    int set_err(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err_ = buf;
+        return code;
+    }
+
+private:
+    bool ok(cudaError_t e, const char* what) {
+        if (e == cudaSuccess) return true;
+        set_err(MOBI_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+        return false;
+    }
+    uint8_t* picture(int s, int idx) const { return ring_ + ((size_t)s * RING + (size_t)(idx % RING)) * pic_; }
+
+    int ensure_out(size_t bytes) {
+        if (bytes <= out_cap_) return MOBI_OK;
+        if (!ok(cudaStreamSynchronize(stream_), "sync")) return MOBI_ERR_CUDA;
+        if (out_d_) cudaFree(out_d_);
+        if (out_h_) cudaFreeHost(out_h_);
+        out_d_ = nullptr; out_h_ = nullptr; out_cap_ = 0;
+        if (!ok(cudaMalloc(&out_d_, bytes), "cudaMalloc(out)")) return MOBI_ERR_NOMEM;
+        if (!ok(cudaMallocHost(&out_h_, bytes), "cudaMallocHost(out)")) return MOBI_ERR_NOMEM;
+        out_cap_ = bytes;
+        return MOBI_OK;
+    }
+    int ensure_arena(Arena& a, size_t bytes) {
+        if (a.pending) {  // the GPU may still be reading the previous contents
+            if (!ok(cudaEventSynchronize(a.consumed), "cudaEventSynchronize")) return MOBI_ERR_CUDA;
+            a.pending = false;
+        }
+        if (bytes <= a.cap) return MOBI_OK;
+        size_t cap = align_up(bytes + bytes / 2, 1 << 16);
+        if (a.h) cudaFreeHost(a.h);
+        if (a.d) cudaFree(a.d);
+        a.h = nullptr; a.d = nullptr; a.cap = 0;
+        if (!ok(cudaMallocHost(&a.h, cap), "cudaMallocHost(arena)")) return MOBI_ERR_NOMEM;
+        if (!ok(cudaMalloc(&a.d, cap), "cudaMalloc(arena)")) return MOBI_ERR_NOMEM;
+        a.cap = cap;
+        return MOBI_OK;
+    }
+
+    // Lay the frames in views_ (hdr == null: stream sits this step out) into arena `a` and build the job
+    // table against ring positions given by `count` (pictures decoded so far, per stream).
+    int pack_step(Arena& a, StepLayout& L, const std::vector<int>& count) {
+        struct Off { size_t hdr, mbs, parts, ops, coefs, intra; };
+        std::vector<Off> off(N_);
+        L = StepLayout();
+        uint32_t max_intra = 0;
+        for (int i = 0; i < N_; i++) if (views_[i].hdr) { L.job_stream.push_back(i); }
+        L.n_jobs = (int)L.job_stream.size();
+        size_t p = 0;
+        L.jobs_off = p; p = align_up(p + sizeof(DevJob) * L.n_jobs, 256);
+        for (int j = 0; j < L.n_jobs; j++) {
+            const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr;
+            L.n_work += h.n_intra;
+            if (h.n_intra > max_intra) max_intra = h.n_intra;
+            if (h.n_intra < h.n_mb) L.n_inter_jobs++;
+            L.mbs += h.n_mb; L.intra_mbs += h.n_intra; L.inter_mbs += h.n_mb - h.n_intra;
+            L.parts += h.n_parts; L.coefs += h.n_coefs; L.ops += h.n_ops;
+        }
+        L.work_off = p; p = align_up(p + sizeof(IntraWork) * L.n_work, 256);
+        for (int j = 0; j < L.n_jobs; j++) {
+            const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr;
+            Off& o = off[j];
+            o.hdr = p; p = align_up(p + sizeof(mobi_frame_hdr), 16);
+            o.mbs = p; p = align_up(p + sizeof(mobi_mb) * h.n_mb, 16);
+            o.parts = p; p = align_up(p + sizeof(mobi_part) * h.n_parts, 16);
+            o.ops = p; p = align_up(p + sizeof(mobi_op) * h.n_ops, 16);
+            o.coefs = p; p = align_up(p + sizeof(mobi_coef) * h.n_coefs + 128, 16);  // +128: the intra kernel prefetches one warp past the end
+            o.intra = p; p = align_up(p + sizeof(uint32_t) * h.n_intra, 256);
+        }
+        L.bytes = p;
+        int rc = ensure_arena(a, L.bytes);
+        if (rc != MOBI_OK) return rc;
+        DevJob* jobs = reinterpret_cast<DevJob*>(a.h + L.jobs_off);
+        pool_.run(L.n_jobs, [&](int j) {
+            const int s = L.job_stream[j];
+            const mobi_packed_frame& f = views_[s];
+            const mobi_frame_hdr& h = *f.hdr;
+            const Off& o = off[j];
+            std::memcpy(a.h + o.hdr, &h, sizeof h);
+            if (h.n_mb) std::memcpy(a.h + o.mbs, f.mbs, sizeof(mobi_mb) * h.n_mb);
+            if (h.n_parts) std::memcpy(a.h + o.parts, f.parts, sizeof(mobi_part) * h.n_parts);
+            if (h.n_ops) std::memcpy(a.h + o.ops, f.ops, sizeof(mobi_op) * h.n_ops);
+            if (h.n_coefs) std::memcpy(a.h + o.coefs, f.coefs, sizeof(mobi_coef) * h.n_coefs);
+            if (h.n_intra) std::memcpy(a.h + o.intra, f.intra_list, sizeof(uint32_t) * h.n_intra);
+            DevJob& J = jobs[j];
+            std::memset(&J, 0, sizeof J);
+            J.hdr = reinterpret_cast<const mobi_frame_hdr*>(a.d + o.hdr);
+            J.mbs = reinterpret_cast<const mobi_mb*>(a.d + o.mbs);
+            J.parts = reinterpret_cast<const mobi_part*>(a.d + o.parts);
+            J.ops = reinterpret_cast<const mobi_op*>(a.d + o.ops);
+            J.coefs = reinterpret_cast<const mobi_coef*>(a.d + o.coefs);
+            J.intra = reinterpret_cast<const uint32_t*>(a.d + o.intra);
+            const int c = count[s];
+            J.dst = picture(s, c);
+            for (int k = 1; k <= 5; k++) J.ref[k - 1] = k <= c ? picture(s, c - k) : nullptr;
+            J.flags = flags_ + (size_t)s * n_mb_;
+            J.n_mb = h.n_mb; J.n_intra = h.n_intra;
+        });
+        // intra work list: rank-major so that tickets of one picture ascend in decode order while
+        // different streams interleave (the wavefronts of all streams advance together)
+        IntraWork* work = reinterpret_cast<IntraWork*>(a.h + L.work_off);
+        uint32_t w = 0;
+        for (uint32_t r = 0; r < max_intra; r++)
+            for (int j = 0; j < L.n_jobs; j++)
+                if (r < views_[L.job_stream[j]].hdr->n_intra) work[w++] = IntraWork{(uint32_t)j, r};
+        return MOBI_OK;
+    }
+    void rebase(uint8_t* h, const StepLayout& L, const uint8_t* from, uint8_t* to) {
+        DevJob* jobs = reinterpret_cast<DevJob*>(h + L.jobs_off);
+        const ptrdiff_t d = to - from;
+        for (int j = 0; j < L.n_jobs; j++) {
+            DevJob& J = jobs[j];
+            J.hdr = reinterpret_cast<const mobi_frame_hdr*>(reinterpret_cast<const uint8_t*>(J.hdr) + d);
+            J.mbs = reinterpret_cast<const mobi_mb*>(reinterpret_cast<const uint8_t*>(J.mbs) + d);
+            J.parts = reinterpret_cast<const mobi_part*>(reinterpret_cast<const uint8_t*>(J.parts) + d);
+            J.ops = reinterpret_cast<const mobi_op*>(reinterpret_cast<const uint8_t*>(J.ops) + d);
+            J.coefs = reinterpret_cast<const mobi_coef*>(reinterpret_cast<const uint8_t*>(J.coefs) + d);
+            J.intra = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(J.intra) + d);
+        }
+    }
+    int launch_step(const uint8_t* d, const StepLayout& L) {
+        const DevJob* jobs = reinterpret_cast<const DevJob*>(d + L.jobs_off);
+        if (L.n_inter_jobs) {
+            if (!ok(launch_inter(jobs, L.n_jobs, g_, stream_), "k_inter")) return MOBI_ERR_CUDA;
+            stats_.launches++;
+        }
+        if (L.n_work) {
+            uint32_t warps = 0;
+            stamp_++;
+            if (!ok(launch_intra(jobs, reinterpret_cast<const IntraWork*>(d + L.work_off), L.n_work, ticket_, ticket_base_, stamp_, g_, sm_count_, stream_, &warps), "k_intra")) return MOBI_ERR_CUDA;
+            ticket_base_ += L.n_work + warps;  // every warp draws exactly one ticket past the end
+            stats_.launches++;
+        }
+        stats_.frames += L.n_jobs; stats_.mbs += L.mbs; stats_.inter_mbs += L.inter_mbs; stats_.intra_mbs += L.intra_mbs;
+        stats_.parts += L.parts; stats_.coefs += L.coefs; stats_.ops += L.ops;
+        return MOBI_OK;
+    }
+
+    // Caller-supplied packed arrays are untrusted: everything the kernels index with is range-checked here.
+    int validate(const mobi_packed_frame& f, int pictures) {
+        const mobi_frame_hdr& h = *f.hdr;
+        if (h.n_mb != n_mb_) return set_err(MOBI_ERR_ARG, "packed frame: n_mb %u, geometry needs %u", h.n_mb, n_mb_);
+        if ((h.n_mb && !f.mbs) || (h.n_parts && !f.parts) || (h.n_ops && !f.ops) || (h.n_coefs && !f.coefs) || (h.n_intra && !f.intra_list))
+            return set_err(MOBI_ERR_ARG, "packed frame: null array");
+        const int S = g_.S, H = (int)H_;
+        uint32_t n_intra = 0;
+        for (uint32_t m = 0; m < h.n_mb; m++) {
+            const mobi_mb& mb = f.mbs[m];
+            const uint32_t kind = mb.info & 3u, nsub = (mb.info >> 2) & 127u, nco = (mb.info >> 9) & 511u;
+            if (kind > 1 || nsub > 64 || nco > 384) return set_err(MOBI_ERR_ARG, "packed frame: MB %u descriptor", m);
+            if ((uint64_t)mb.first_coef + nco > h.n_coefs) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient range", m);
+            if (kind == 1) {
+                if ((uint64_t)mb.first_sub + nsub > h.n_ops) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op range", m);
+                if (mb.intra_rank >= h.n_intra || f.intra_list[mb.intra_rank] != m) return set_err(MOBI_ERR_ARG, "packed frame: MB %u intra rank", m);
+                n_intra++;
+                continue;
+            }
+            if (nsub == 0 || (uint64_t)mb.first_sub + nsub > h.n_parts) return set_err(MOBI_ERR_ARG, "packed frame: MB %u partition range", m);
+            const int mbx = (int)(m % (uint32_t)g_.mbw), mby = (int)(m / (uint32_t)g_.mbw);
+            uint64_t cover[4] = {0, 0, 0, 0};  // 16x16 luma pixels
+            for (uint32_t k = 0; k < nsub; k++) {
+                const mobi_part& p = f.parts[mb.first_sub + k];
+                const int x = (p.xy & 15) * 2, y = (p.xy >> 4) * 2, w = 2 << (p.shape & 3), hh = 2 << ((p.shape >> 2) & 3), ref = p.shape >> 4;
+                if (x + w > 16 || y + hh > 16) return set_err(MOBI_ERR_ARG, "packed frame: MB %u partition geometry", m);
+                if (ref < 1 || ref > 5 || ref > pictures) return set_err(MOBI_ERR_REFERENCE, "packed frame: MB %u references picture %d of %d", m, ref, pictures);
+                const long long offp = (long long)(mby * 16 + y) * S + mbx * 16 + x;
+                const int dx = p.mvx, dy = p.mvy;
+                const long long first = offp + (long long)(dy >> 1) * S + (dx >> 1);
+                const long long last = first + (long long)(hh - 1 + (dy & 1)) * S + w - 1 + (dx & 1);
+                if (first < 0 || last >= (long long)S * H) return set_err(MOBI_ERR_RANGE, "packed frame: MB %u luma vector", m);
+                const int cdx = dx >> 1, cdy = dy >> 1;
+                const long long cfirst = offp / 2 + (long long)(cdy >> 1) * S + (cdx >> 1);
+                const long long clast = cfirst + S / 2 + (long long)((hh >> 1) - 1 + (cdy & 1)) * S + (w >> 1) - 1 + (cdx & 1);
+                if (cfirst < 0 || clast >= (long long)S * H / 2) return set_err(MOBI_ERR_RANGE, "packed frame: MB %u chroma vector", m);
+                for (int yy = y; yy < y + hh; yy++) cover[yy >> 2] |= (uint64_t)((1u << w) - 1u) << ((yy & 3) * 16 + x);
+            }
+            for (int k = 0; k < 4; k++) if (cover[k] != ~0ull) return set_err(MOBI_ERR_ARG, "packed frame: MB %u partitions do not tile the macroblock", m);
+        }
+        if (n_intra != h.n_intra) return set_err(MOBI_ERR_ARG, "packed frame: intra count");
+        for (uint32_t k = 0; k < h.n_coefs; k++) {
+            const mobi_coef& c = f.coefs[k];
+            if ((c.blk & 7) > 5) return set_err(MOBI_ERR_ARG, "packed frame: coefficient %u block tag", k);
+            if (!(c.blk & 0x80) && (c.pos & 63) > 15) return set_err(MOBI_ERR_ARG, "packed frame: coefficient %u scan position", k);
+        }
+        for (int k = 0; k < 80; k++) {
+            const uint32_t idx = h.qtab[k] & 0xFF;
+            if (idx >= (k < 64 ? 64u : 16u)) return set_err(MOBI_ERR_ARG, "packed frame: scan table entry %d", k);
+        }
+        return MOBI_OK;
+    }
+
+    uint32_t W_, H_;
+    int ver_, dev_, N_;
+    Geom g_;
+    uint32_t n_mb_;
+    size_t ysz_, pic_;
+    int sm_count_ = 148;
+    Pool pool_;
+    std::vector<std::unique_ptr<Parser>> parsers_;
+    std::vector<ParsedFrame> frames_;
+    std::vector<mobi_packed_frame> views_;
+    std::vector<int> rc_;
+    std::vector<int> count_, staged_count_;
+    cudaStream_t stream_ = nullptr;
+    uint8_t* ring_ = nullptr;
+    uint32_t* flags_ = nullptr;
+    uint32_t* ticket_ = nullptr;
+    uint32_t ticket_base_ = 0, stamp_ = 0;
+    Arena arena_[2];
+    int cur_arena_ = 0;
+    std::vector<Staged> staged_;
+    uint8_t* out_d_ = nullptr;
+    uint8_t* out_h_ = nullptr;
+    size_t out_cap_ = 0;
+    const uint8_t** ptr_d_ = nullptr;
+    const uint8_t** ptr_h_ = nullptr;
+    mobi_batch_stats stats_{};
+    uint32_t quant_override_ = 0, yuv_override_ = 0;
+    bool have_override_ = false;
+    std::string err_;
+};
+
+}  // namespace mobi
+
+// ---- C ABI ---------------------------------------------------------------------------------------
+struct mobi_batch { mobi::Batch b; mobi_batch(uint32_t w, uint32_t h, int v, int dev, int n, int t) : b(w, h, v, dev, n, t) {} };
+struct mobi_decoder { mobi::Batch b; mobi_decoder(uint32_t w, uint32_t h, int v, int dev) : b(w, h, v, dev, 1, 1) {} };
+
+namespace {
+int check_geometry(uint32_t w, uint32_t h, int version) {
+    if (w == 0 || h == 0 || (w & 15) || (h & 15) || w > 1024 || h > 1024) return MOBI_ERR_ARG;
+    if (version == MOBI_VXDS) return MOBI_ERR_UNSUPPORTED;
+    if (version != MOBI_MODSDS && version != MOBI_MOFLEX3DS) return MOBI_ERR_ARG;
+    return MOBI_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mobi_create(uint32_t width, uint32_t height, int version, int device, mobi_t** out) {
+    if (!out) return MOBI_ERR_ARG;
+    *out = nullptr;
+    int rc = check_geometry(width, height, version);
+    if (rc != MOBI_OK) return rc;
+    mobi_decoder* d;
+    try { d = new mobi_decoder(width, height, version, device); } catch (...) { return MOBI_ERR_NOMEM; }
+    rc = d->b.init();
+    if (rc != MOBI_OK) { fprintf(stderr, "mobicuda: %s\n", d->b.error()); delete d; return rc; }
+    *out = d;
+    return MOBI_OK;
+}
+void mobi_destroy(mobi_t* d) { delete d; }
+
+int mobi_decode_frame(mobi_t* d, const uint8_t* data, int len, int* offset_inout) {
+    if (!d) return MOBI_ERR_ARG;
+    try { int st = 0; return d->b.decode(&data, &len, offset_inout, &st); } catch (...) { return d->b.set_err(MOBI_ERR_NOMEM, "out of host memory"); }
+}
+int mobi_submit_packed(mobi_t* d, const mobi_packed_frame* f) {
+    if (!d) return MOBI_ERR_ARG;
+    try { return d->b.submit(0, f); } catch (...) { return d->b.set_err(MOBI_ERR_NOMEM, "out of host memory"); }
+}
+int mobi_read_planes_strided(mobi_t* d, uint8_t* y, uint8_t* uv) { return d ? d->b.read_strided(0, y, uv) : MOBI_ERR_ARG; }
+int mobi_read_yuv(mobi_t* d, uint8_t* y, uint8_t* u, uint8_t* v) { return d ? d->b.read_yuv_one(0, y, u, v) : MOBI_ERR_ARG; }
+int mobi_read_bgra(mobi_t* d, uint8_t* dst, int dst_stride) { return d ? d->b.read_bgra_one(0, dst, dst_stride) : MOBI_ERR_ARG; }
+int mobi_get_state(const mobi_t* d, uint32_t* quantizer, uint32_t* yuv_format, int* stride) {
+    if (!d) return MOBI_ERR_ARG;
+    d->b.get_state(0, quantizer, yuv_format, stride);
+    return MOBI_OK;
+}
+const char* mobi_last_error(const mobi_t* d) { return d ? d->b.error() : "null decoder"; }
+
+int mobi_batch_create(uint32_t width, uint32_t height, int version, int device, int n_streams, int n_threads, mobi_batch_t** out) {
+    if (!out) return MOBI_ERR_ARG;
+    *out = nullptr;
+    int rc = check_geometry(width, height, version);
+    if (rc != MOBI_OK) return rc;
+    if (n_streams < 1 || n_streams > 65535) return MOBI_ERR_ARG;
+    if (n_threads <= 0) { n_threads = (int)std::thread::hardware_concurrency(); if (n_threads < 1) n_threads = 1; }
+    if (n_threads > n_streams) n_threads = n_streams;
+    mobi_batch* b;
+    try { b = new mobi_batch(width, height, version, device, n_streams, n_threads); } catch (...) { return MOBI_ERR_NOMEM; }
+    rc = b->b.init();
+    if (rc != MOBI_OK) { fprintf(stderr, "mobicuda: %s\n", b->b.error()); delete b; return rc; }
+    *out = b;
+    return MOBI_OK;
+}
+void mobi_batch_destroy(mobi_batch_t* b) { delete b; }
+int mobi_batch_decode(mobi_batch_t* b, const uint8_t* const* data, const int* len, int* offset_inout, int* status) {
+    if (!b) return MOBI_ERR_ARG;
+    try { return b->b.decode(data, len, offset_inout, status); } catch (...) { return b->b.set_err(MOBI_ERR_NOMEM, "out of host memory"); }
+}
+int mobi_batch_read_yuv(mobi_batch_t* b, uint8_t* dst) { return b ? b->b.read_yuv_all(dst) : MOBI_ERR_ARG; }
+int mobi_batch_read_planes_strided(mobi_batch_t* b, int stream, uint8_t* y, uint8_t* uv) { return b ? b->b.read_strided(stream, y, uv) : MOBI_ERR_ARG; }
+int mobi_batch_read_bgra(mobi_batch_t* b, int stream, uint8_t* dst, int dst_stride) { return b ? b->b.read_bgra_one(stream, dst, dst_stride) : MOBI_ERR_ARG; }
+int mobi_batch_read_bgra_all(mobi_batch_t* b, uint8_t* dst) { return b ? b->b.bgra_all(dst) : MOBI_ERR_ARG; }
+const char* mobi_batch_last_error(const mobi_batch_t* b) { return b ? b->b.error() : "null batch"; }
+int mobi_batch_stage(mobi_batch_t* b, const uint8_t* const* data, const int* len, int* offset_inout) {
+    if (!b) return MOBI_ERR_ARG;
+    try { return b->b.stage(data, len, offset_inout); } catch (...) { return b->b.set_err(MOBI_ERR_NOMEM, "out of host memory"); }
+}
+int mobi_batch_replay(mobi_batch_t* b, int first, int count) { return b ? b->b.replay(first, count) : MOBI_ERR_ARG; }
+int mobi_batch_staged_steps(const mobi_batch_t* b) { return b ? b->b.staged_steps() : 0; }
+void mobi_batch_clear_staged(mobi_batch_t* b) { if (b) b->b.clear_staged(); }
+int mobi_batch_reset(mobi_batch_t* b) { return b ? b->b.reset(false) : MOBI_ERR_ARG; }
+int mobi_batch_reset_streams(mobi_batch_t* b) { return b ? b->b.reset(true) : MOBI_ERR_ARG; }
+int mobi_batch_sync(mobi_batch_t* b) { return b ? b->b.sync() : MOBI_ERR_ARG; }
+void* mobi_batch_cuda_stream(mobi_batch_t* b) { return b ? b->b.cuda_stream() : nullptr; }
+int mobi_batch_get_stats(const mobi_batch_t* b, mobi_batch_stats* st) {
+    if (!b || !st) return MOBI_ERR_ARG;
+    *st = b->b.stats();
+    return MOBI_OK;
+}
+void mobi_batch_clear_stats(mobi_batch_t* b) { if (b) b->b.clear_stats(); }
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libmobicuda.so via ctypes), against the CPU
+oracle on the same seeded inputs.  Bit-exact on Y, U, V (strided planes incl. padding), on Offset/Quantizer, and
+on the BGRA bitmap (binary32, source order; tolerance 0)."""
+import numpy as np
+import pytest
+
+from mobiclipdecoder_b200 import MobiBatch, MobiclipDecoder, MobiParser
+from mobiclipdecoder_b200.workloads import CONFIGS, frames, make_stream
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _diff_report(a, b, S):
+    idx = np.flatnonzero(a != b)
+    if idx.size == 0:
+        return 'equal'
+    return '%d bytes differ; first at flat %d (row %d, col %d): got %d want %d' % (idx.size, idx[0], idx[0] // S, idx[0] % S, a[idx[0]], b[idx[0]])
+
+
+@pytest.mark.parametrize('name,n_frames', [('mods_256x192', 64), ('pframes_256x192', 24), ('moflex_400x240', 100), ('moc5_640x480', 34)])
+def test_single_stream_bit_exact(name, n_frames):
+    w, h, ver, _ = CONFIGS[name]
+    fr = frames(name, 0xC0FFEE, n_frames)
+    dec = MobiclipDecoder(w, h, ver)
+    ora = Oracle(w, h, ver)
+    for i, (data, key) in enumerate(fr):
+        dec.Data, dec.Offset = data, 0
+        bmp = dec.DecodeFrame()
+        ok, off, want_bmp = ora.decode(data, 0)
+        assert ok, 'generator produced an out-of-contract frame %d' % i
+        assert bmp is not None, 'frame %d: %s' % (i, dec.last_error())
+        assert dec.Offset == off
+        assert dec.Quantizer == ora.quantizer and dec.YuvFormat == ora.yuvformat
+        y, uv = dec.Y[0], dec.UV[0]
+        assert np.array_equal(y, ora.y), 'frame %d (%s) luma: %s' % (i, 'I' if key else 'P', _diff_report(y, ora.y, dec.Stride))
+        assert np.array_equal(uv, ora.uv), 'frame %d (%s) chroma: %s' % (i, 'I' if key else 'P', _diff_report(uv, ora.uv, dec.Stride))
+        assert np.array_equal(bmp, want_bmp), 'frame %d bitmap differs' % i
+    ty, tu, tv = dec.ReadYuv()
+    oy, ou, ov = ora.crop()
+    assert np.array_equal(ty, oy) and np.array_equal(tu, ou) and np.array_equal(tv, ov)
+    dec.close()
+
+
+def test_batch_lockstep_bit_exact():
+    name, n_streams, n_frames = 'moflex_400x240', 12, 20
+    w, h, ver, _ = CONFIGS[name]
+    streams = [frames(name, 100 + s, n_frames, gop=7 + s % 3) for s in range(n_streams)]
+    oracles = [Oracle(w, h, ver) for _ in range(n_streams)]
+    b = MobiBatch(w, h, ver, n_streams, n_threads=4)
+    for f in range(n_frames):
+        offs, status = b.decode([streams[s][f][0] for s in range(n_streams)])
+        assert all(st == 0 for st in status)
+        got = b.read_yuv()
+        for s in range(n_streams):
+            ok, off, _ = oracles[s].decode(streams[s][f][0], 0, False)
+            assert ok and offs[s] == off
+            assert np.array_equal(got[s], oracles[s].i420()), 'stream %d frame %d' % (s, f)
+    bg = b.read_bgra_all()
+    for s in range(n_streams):
+        assert np.array_equal(bg[s], b.read_bgra(s))
+    b.close()
+
+
+def test_staged_replay_matches_live_decode():
+    name, n_streams, n_frames = 'pframes_256x192', 16, 12
+    w, h, ver, _ = CONFIGS[name]
+    streams = [frames(name, 1 + s, n_frames) for s in range(n_streams)]
+    b = MobiBatch(w, h, ver, n_streams, n_threads=2)
+    for f in range(n_frames):
+        b.stage([streams[s][f][0] for s in range(n_streams)])
+    assert b.staged_steps() == n_frames
+    oracles = [Oracle(w, h, ver) for _ in range(n_streams)]
+    for s in range(n_streams):
+        for f in range(n_frames):
+            assert oracles[s].decode(streams[s][f][0], 0, False)[0]
+    want = np.stack([o.i420() for o in oracles])
+    for _ in range(2):  # replay twice: the second pass must not depend on leftovers of the first
+        b.reset()
+        b.replay(0, n_frames)
+        assert np.array_equal(b.read_yuv(), want)
+    st = b.stats()
+    assert st['frames'] == 2 * n_streams * n_frames and st['launches'] > 0
+    b.close()
+
+
+def test_submit_packed_path():
+    name = 'pframes_256x192'
+    w, h, ver, _ = CONFIGS[name]
+    fr = frames(name, 77, 6)
+    dec, par, ora = MobiclipDecoder(w, h, ver), MobiParser(w, h, ver), Oracle(w, h, ver)
+    for data, key in fr:
+        rc, off, pf = par.parse(data, 0)
+        assert rc == 0
+        dec.SubmitPacked(pf)
+        assert ora.decode(data, 0, False)[0]
+        assert np.array_equal(dec.Y[0], ora.y) and np.array_equal(dec.UV[0], ora.uv)
+    dec.close()
+
+
+def test_error_behaviour_matches_reference_null():
+    w, h, ver, _ = CONFIGS['moflex_400x240']
+    fr = frames('moflex_400x240', 5, 3)
+    dec, ora = MobiclipDecoder(w, h, ver), Oracle(w, h, ver)
+    # a P-frame before any picture exists: Y[1] == null -> exception -> null bitmap (MD:413, 325)
+    dec.Data, dec.Offset = fr[1][0], 0
+    assert dec.DecodeFrame() is None and dec.last_status == -4
+    assert not ora.decode(fr[1][0], 0, False)[0]
+    # truncated payload
+    dec.Data, dec.Offset = fr[0][0][:40], 0
+    assert dec.DecodeFrame() is None
+    # the decoder is still usable and exact afterwards
+    ora = Oracle(w, h, ver)
+    for data, _ in fr:
+        dec.Data, dec.Offset = data, 0
+        assert dec.DecodeFrame() is not None
+        assert ora.decode(data, 0, False)[0]
+    assert np.array_equal(dec.Y[0], ora.y) and np.array_equal(dec.UV[0], ora.uv)
+    dec.close()
