@@ -13,6 +13,7 @@
  */
 #ifndef MOBICUDA_H
 #define MOBICUDA_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -49,7 +50,8 @@ typedef struct mobi_frame_hdr {
     uint32_t quantizer, yuv_format;
     uint32_t bytes_consumed; /* value of Offset after the call, relative to the Offset passed in */
     uint32_t max_ref;      /* highest ring index referenced (0 for I-frames) */
-    uint32_t reserved[6];
+    uint32_t n_inter_coefs; /* coefficients that belong to inter macroblocks (accounting only) */
+    uint32_t reserved[5];
     uint32_t qtab[80];
 } mobi_frame_hdr;            /* 384 bytes */
 
@@ -156,6 +158,18 @@ int mobi_batch_read_bgra(mobi_batch_t* b, int stream, uint8_t* dst, int dst_stri
 int mobi_batch_read_bgra_all(mobi_batch_t* b, uint8_t* dst);
 const char* mobi_batch_last_error(const mobi_batch_t* b);
 
+/* --- pipelined decode: the host parses step k+1 while the GPU reconstructs, converts and copies back step k.
+ * mobi_batch_submit = mobi_batch_decode + conversion of every stream's new picture (format MOBI_OUT_I420: tight
+ * planar Y,U,V, W*H*3/2 bytes per stream; MOBI_OUT_BGRA: the Bitmap of MD:260-323, W*H*4 bytes per stream) + an
+ * asynchronous copy into pinned host memory.  It returns without waiting for the GPU.  At most two results may be
+ * outstanding.  mobi_batch_fetch waits for the OLDEST outstanding result: dst (optional) receives a copy,
+ * *view (optional) the library's pinned buffer itself (valid until the second mobi_batch_submit from now),
+ * *bytes (optional) its size. --- */
+#define MOBI_OUT_I420 1
+#define MOBI_OUT_BGRA 2
+int mobi_batch_submit(mobi_batch_t* b, const uint8_t* const* data, const int* len, int* offset_inout, int* status, int format);
+int mobi_batch_fetch(mobi_batch_t* b, uint8_t* dst, const uint8_t** view, size_t* bytes);
+
 /* --- pre-parsed, device-resident replay (bench "value" leg / ncu captures): frames are parsed and
  * uploaded once with mobi_batch_stage(), then mobi_batch_replay() runs reconstruction only. --- */
 /* Parse + upload step `step` of every stream (data/len/offset as above) into resident staging. */
@@ -177,8 +191,14 @@ typedef struct mobi_batch_stats {
     uint64_t launches;        /* kernels launched */
     uint64_t frames, mbs, inter_mbs, intra_mbs, parts, coefs, ops;
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t inter_coefs;     /* of coefs: those of inter macroblocks */
 } mobi_batch_stats;
 int mobi_batch_get_stats(const mobi_batch_t* b, mobi_batch_stats* st);
+/* Per-kernel device time, for roofline accounting: while enabled every reconstruction kernel launch is bracketed
+ * by CUDA events on the batch's stream.  mobi_batch_get_kernel_times synchronises, returns the summed durations
+ * (milliseconds) and launch counts since the last call, and clears them. */
+int mobi_batch_set_kernel_timing(mobi_batch_t* b, int enabled);
+int mobi_batch_get_kernel_times(mobi_batch_t* b, double* inter_ms, uint64_t* inter_launches, double* intra_ms, uint64_t* intra_launches);
 void mobi_batch_clear_stats(mobi_batch_t* b);
 
 int mobicuda_abi_version(void);

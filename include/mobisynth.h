@@ -40,6 +40,8 @@ typedef struct mobi_synth_params {
     float p_oob_mv;           /* probability of letting a vector read outside the visible picture
                                  (still inside the flat arrays: exercises stride padding / row wrap) */
     int32_t inter_only;       /* 1: P-frames carry no intra MBs (BASELINE config 2) */
+    int32_t gop_phase;        /* I-frames fall where (frame index + gop_phase) % gop == 0 (frame 0 is always I):
+                                 staggers the keyframes of streams that advance in lock step */
 } mobi_synth_params;
 
 /* Fills *p with the defaults used for BASELINE configs 1/3. */

@@ -10,7 +10,7 @@ u8p = C.POINTER(C.c_uint8)
 class FrameHdr(C.Structure):
     _fields_ = [('flags', C.c_uint32), ('n_mb', C.c_uint32), ('n_parts', C.c_uint32), ('n_ops', C.c_uint32),
                 ('n_coefs', C.c_uint32), ('n_intra', C.c_uint32), ('quantizer', C.c_uint32), ('yuv_format', C.c_uint32),
-                ('bytes_consumed', C.c_uint32), ('max_ref', C.c_uint32), ('reserved', C.c_uint32 * 6), ('qtab', C.c_uint32 * 80)]
+                ('bytes_consumed', C.c_uint32), ('max_ref', C.c_uint32), ('n_inter_coefs', C.c_uint32), ('reserved', C.c_uint32 * 5), ('qtab', C.c_uint32 * 80)]
 
 
 class Mb(C.Structure):
@@ -31,7 +31,7 @@ class PackedFrame(C.Structure):
 
 
 class BatchStats(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ('launches', 'frames', 'mbs', 'inter_mbs', 'intra_mbs', 'parts', 'coefs', 'ops', 'h2d_bytes', 'd2h_bytes')]
+    _fields_ = [(n, C.c_uint64) for n in ('launches', 'frames', 'mbs', 'inter_mbs', 'intra_mbs', 'parts', 'coefs', 'ops', 'h2d_bytes', 'd2h_bytes', 'inter_coefs')]
 
 
 # every symbol include/mobicuda.h declares: name -> (restype, argtypes)
@@ -53,6 +53,8 @@ MOBICUDA_EXPORTS = {
     'mobi_batch_create': (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     'mobi_batch_destroy': (None, [C.c_void_p]),
     'mobi_batch_decode': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'mobi_batch_submit': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
+    'mobi_batch_fetch': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     'mobi_batch_read_yuv': (C.c_int, [C.c_void_p, C.c_void_p]),
     'mobi_batch_read_planes_strided': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'mobi_batch_read_bgra': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -68,6 +70,8 @@ MOBICUDA_EXPORTS = {
     'mobi_batch_cuda_stream': (C.c_void_p, [C.c_void_p]),
     'mobi_batch_get_stats': (C.c_int, [C.c_void_p, C.POINTER(BatchStats)]),
     'mobi_batch_clear_stats': (None, [C.c_void_p]),
+    'mobi_batch_set_kernel_timing': (C.c_int, [C.c_void_p, C.c_int]),
+    'mobi_batch_get_kernel_times': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
 
 
@@ -75,7 +79,7 @@ class SynthParamsC(C.Structure):
     _fields_ = [('width', C.c_uint32), ('height', C.c_uint32), ('version', C.c_int32), ('seed', C.c_uint64), ('gop', C.c_int32),
                 ('quant', C.c_int32), ('p_dquant', C.c_float), ('p_split', C.c_float), ('p_intra_mb', C.c_float), ('p_sub_mb', C.c_float),
                 ('p_cbp', C.c_float), ('p_blk8', C.c_float), ('mean_coefs', C.c_float), ('p_escape', C.c_float), ('mv_range', C.c_int32),
-                ('p_ref1', C.c_float), ('p_zero_mv', C.c_float), ('p_oob_mv', C.c_float), ('inter_only', C.c_int32)]
+                ('p_ref1', C.c_float), ('p_zero_mv', C.c_float), ('p_oob_mv', C.c_float), ('inter_only', C.c_int32), ('gop_phase', C.c_int32)]
 
 
 class SynthStats(C.Structure):

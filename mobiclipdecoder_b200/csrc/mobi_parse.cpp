@@ -355,6 +355,7 @@ struct FrameParse {
         mb.info = 0u | np << 2 | nco << 9 | mask << 18;
         mb.first_sub = first_part; mb.first_coef = first_coef; mb.intra_rank = 0;
         out.mbs.push_back(mb);
+        out.hdr.n_inter_coefs += nco;
     }
 
     static int med3(int a, int c, int e) {  // MD:171-188

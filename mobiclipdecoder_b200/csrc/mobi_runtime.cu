@@ -106,12 +106,22 @@ struct StepLayout {
     int n_jobs = 0, n_inter_jobs = 0;
     uint32_t n_work = 0;
     std::vector<int> job_stream;  // stream index of each job
-    uint64_t mbs = 0, inter_mbs = 0, intra_mbs = 0, parts = 0, coefs = 0, ops = 0;
+    uint64_t mbs = 0, inter_mbs = 0, intra_mbs = 0, parts = 0, coefs = 0, ops = 0, inter_coefs = 0;
 };
 
 struct Staged {
     uint8_t* d = nullptr;
     StepLayout L;
+};
+
+// One in-flight result of the pipelined path: converted on the device, copied to pinned host memory.
+struct OutSlot {
+    uint8_t* h = nullptr;
+    uint8_t* d = nullptr;
+    const uint8_t** ptr_h = nullptr;
+    const uint8_t** ptr_d = nullptr;
+    size_t cap = 0, bytes = 0;
+    cudaEvent_t ready = nullptr;
 };
 
 }  // namespace
@@ -144,6 +154,15 @@ public:
             if (out_h_) cudaFreeHost(out_h_);
             if (ptr_d_) cudaFree(ptr_d_);
             if (ptr_h_) cudaFreeHost(ptr_h_);
+            for (int w = 0; w < 2; w++) for (cudaEvent_t e : ev_[w]) cudaEventDestroy(e);
+            for (cudaEvent_t e : ev_free_) cudaEventDestroy(e);
+            for (auto& o : slot_) {
+                if (o.h) cudaFreeHost(o.h);
+                if (o.d) cudaFree(o.d);
+                if (o.ptr_h) cudaFreeHost(o.ptr_h);
+                if (o.ptr_d) cudaFree(o.ptr_d);
+                if (o.ready) cudaEventDestroy(o.ready);
+            }
             cudaStreamDestroy(stream_);
         }
     }
@@ -367,6 +386,91 @@ public:
         return sync();
     }
 
+    // ---- pipelined path: submit step k+1 while step k is still on the GPU ---------------------------
+    // format: 1 = tight I420, 2 = BGRA.  At most two results may be outstanding.
+    int submit_async(const uint8_t* const* data, const int* len, int* offset, int* status, int format) {
+        if (format != 1 && format != 2) return set_err(MOBI_ERR_ARG, "output format must be 1 (I420) or 2 (BGRA)");
+        if (slots_used_ == 2) return set_err(MOBI_ERR_STATE, "two results outstanding: fetch one first");
+        int rc = decode(data, len, offset, status);
+        if (rc != MOBI_OK) return rc;
+        OutSlot& o = slot_[slot_head_];
+        const size_t per = format == 1 ? (size_t)W_ * H_ * 3 / 2 : (size_t)W_ * H_ * 4, total = per * N_;
+        if (o.cap < total) {
+            if (o.h) cudaFreeHost(o.h);
+            if (o.d) cudaFree(o.d);
+            o.h = nullptr; o.d = nullptr; o.cap = 0;
+            if (!ok(cudaMallocHost(&o.h, total), "cudaMallocHost(result)")) return MOBI_ERR_NOMEM;
+            if (!ok(cudaMalloc(&o.d, total), "cudaMalloc(result)")) return MOBI_ERR_NOMEM;
+            o.cap = total;
+        }
+        if (!o.ptr_h) {
+            if (!ok(cudaMallocHost(&o.ptr_h, sizeof(void*) * N_), "cudaMallocHost(ptrs)")) return MOBI_ERR_NOMEM;
+            if (!ok(cudaMalloc(&o.ptr_d, sizeof(void*) * N_), "cudaMalloc(ptrs)")) return MOBI_ERR_NOMEM;
+            if (!ok(cudaEventCreateWithFlags(&o.ready, cudaEventDisableTiming), "cudaEventCreate")) return MOBI_ERR_CUDA;
+        }
+        for (int s = 0; s < N_; s++) {
+            if (count_[s] == 0) return set_err(MOBI_ERR_STATE, "stream %d: no picture decoded yet", s);
+            o.ptr_h[s] = picture(s, count_[s] - 1);
+        }
+        if (!ok(cudaMemcpyAsync(o.ptr_d, o.ptr_h, sizeof(void*) * N_, cudaMemcpyHostToDevice, stream_), "H2D ptrs")) return MOBI_ERR_CUDA;
+        if (format == 1) { if (!ok(launch_pack_i420(o.ptr_d, N_, o.d, g_, stream_), "k_pack_i420")) return MOBI_ERR_CUDA; }
+        else { if (!ok(launch_bgra(o.ptr_d, N_, o.d, (int)W_ * 4, per, g_, stream_), "k_bgra")) return MOBI_ERR_CUDA; }
+        stats_.launches++;
+        if (!ok(cudaMemcpyAsync(o.h, o.d, total, cudaMemcpyDeviceToHost, stream_), "D2H result")) return MOBI_ERR_CUDA;
+        stats_.d2h_bytes += total;
+        stats_.h2d_bytes += sizeof(void*) * N_;
+        if (!ok(cudaEventRecord(o.ready, stream_), "cudaEventRecord")) return MOBI_ERR_CUDA;
+        o.bytes = total;
+        slot_head_ ^= 1;
+        slots_used_++;
+        return MOBI_OK;
+    }
+    // Oldest outstanding result.  dst != null: copied there; *view (optional) receives the pinned buffer, valid
+    // until the second submit_async from now.
+    int fetch(uint8_t* dst, const uint8_t** view, size_t* bytes) {
+        if (slots_used_ == 0) return set_err(MOBI_ERR_STATE, "no result outstanding");
+        if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        OutSlot& o = slot_[(slot_head_ + 2 - slots_used_) & 1];
+        if (!ok(cudaEventSynchronize(o.ready), "cudaEventSynchronize")) return MOBI_ERR_CUDA;
+        slots_used_--;
+        if (dst) {
+            const size_t per = o.bytes / N_;
+            pool_.run(N_, [&](int i) { std::memcpy(dst + per * i, o.h + per * i, per); });
+        }
+        if (view) *view = o.h;
+        if (bytes) *bytes = o.bytes;
+        return MOBI_OK;
+    }
+
+    // ---- per-kernel timing (roofline accounting) ---------------------------------------------------
+    void set_timing(bool on) { timing_ = on; }
+    void tick(int which) {
+        cudaEvent_t e;
+        if (ev_free_.empty()) cudaEventCreate(&e); else { e = ev_free_.back(); ev_free_.pop_back(); }
+        cudaEventRecord(e, stream_);
+        ev_[which].push_back(e);
+    }
+    int kernel_times(double* inter_ms, uint64_t* inter_n, double* intra_ms, uint64_t* intra_n) {
+        int rc = sync();
+        if (rc != MOBI_OK) return rc;
+        double ms[2] = {0, 0};
+        uint64_t n[2] = {0, 0};
+        for (int w = 0; w < 2; w++) {
+            for (size_t i = 0; i + 1 < ev_[w].size(); i += 2) {
+                float t = 0;
+                cudaEventElapsedTime(&t, ev_[w][i], ev_[w][i + 1]);
+                ms[w] += t; n[w]++;
+            }
+            for (cudaEvent_t e : ev_[w]) ev_free_.push_back(e);
+            ev_[w].clear();
+        }
+        if (inter_ms) *inter_ms = ms[0];
+        if (inter_n) *inter_n = n[0];
+        if (intra_ms) *intra_ms = ms[1];
+        if (intra_n) *intra_n = n[1];
+        return MOBI_OK;
+    }
+
     void get_state(int s, uint32_t* q, uint32_t* yf, int* stride) const {
         if (q) *q = have_override_ ? quant_override_ : parsers_[s]->quantizer();
         if (yf) *yf = have_override_ ? yuv_override_ : parsers_[s]->yuv_format();
@@ -438,7 +542,7 @@ private:
             if (h.n_intra > max_intra) max_intra = h.n_intra;
             if (h.n_intra < h.n_mb) L.n_inter_jobs++;
             L.mbs += h.n_mb; L.intra_mbs += h.n_intra; L.inter_mbs += h.n_mb - h.n_intra;
-            L.parts += h.n_parts; L.coefs += h.n_coefs; L.ops += h.n_ops;
+            L.parts += h.n_parts; L.coefs += h.n_coefs; L.ops += h.n_ops; L.inter_coefs += h.n_inter_coefs;
         }
         L.work_off = p; p = align_up(p + sizeof(IntraWork) * L.n_work, 256);
         for (int j = 0; j < L.n_jobs; j++) {
@@ -505,18 +609,22 @@ private:
     int launch_step(const uint8_t* d, const StepLayout& L) {
         const DevJob* jobs = reinterpret_cast<const DevJob*>(d + L.jobs_off);
         if (L.n_inter_jobs) {
+            if (timing_) tick(0);
             if (!ok(launch_inter(jobs, L.n_jobs, g_, stream_), "k_inter")) return MOBI_ERR_CUDA;
+            if (timing_) tick(0);
             stats_.launches++;
         }
         if (L.n_work) {
             uint32_t warps = 0;
             stamp_++;
+            if (timing_) tick(1);
             if (!ok(launch_intra(jobs, reinterpret_cast<const IntraWork*>(d + L.work_off), L.n_work, ticket_, ticket_base_, stamp_, g_, sm_count_, stream_, &warps), "k_intra")) return MOBI_ERR_CUDA;
+            if (timing_) tick(1);
             ticket_base_ += L.n_work + warps;  // every warp draws exactly one ticket past the end
             stats_.launches++;
         }
         stats_.frames += L.n_jobs; stats_.mbs += L.mbs; stats_.inter_mbs += L.inter_mbs; stats_.intra_mbs += L.intra_mbs;
-        stats_.parts += L.parts; stats_.coefs += L.coefs; stats_.ops += L.ops;
+        stats_.parts += L.parts; stats_.coefs += L.coefs; stats_.ops += L.ops; stats_.inter_coefs += L.inter_coefs;
         return MOBI_OK;
     }
 
@@ -598,6 +706,10 @@ private:
     size_t out_cap_ = 0;
     const uint8_t** ptr_d_ = nullptr;
     const uint8_t** ptr_h_ = nullptr;
+    bool timing_ = false;
+    std::vector<cudaEvent_t> ev_[2], ev_free_;
+    OutSlot slot_[2];
+    int slot_head_ = 0, slots_used_ = 0;
     mobi_batch_stats stats_{};
     uint32_t quant_override_ = 0, yuv_override_ = 0;
     bool have_override_ = false;
@@ -673,6 +785,11 @@ int mobi_batch_decode(mobi_batch_t* b, const uint8_t* const* data, const int* le
     if (!b) return MOBI_ERR_ARG;
     try { return b->b.decode(data, len, offset_inout, status); } catch (...) { return b->b.set_err(MOBI_ERR_NOMEM, "out of host memory"); }
 }
+int mobi_batch_submit(mobi_batch_t* b, const uint8_t* const* data, const int* len, int* offset_inout, int* status, int format) {
+    if (!b) return MOBI_ERR_ARG;
+    try { return b->b.submit_async(data, len, offset_inout, status, format); } catch (...) { return b->b.set_err(MOBI_ERR_NOMEM, "out of host memory"); }
+}
+int mobi_batch_fetch(mobi_batch_t* b, uint8_t* dst, const uint8_t** view, size_t* bytes) { return b ? b->b.fetch(dst, view, bytes) : MOBI_ERR_ARG; }
 int mobi_batch_read_yuv(mobi_batch_t* b, uint8_t* dst) { return b ? b->b.read_yuv_all(dst) : MOBI_ERR_ARG; }
 int mobi_batch_read_planes_strided(mobi_batch_t* b, int stream, uint8_t* y, uint8_t* uv) { return b ? b->b.read_strided(stream, y, uv) : MOBI_ERR_ARG; }
 int mobi_batch_read_bgra(mobi_batch_t* b, int stream, uint8_t* dst, int dst_stride) { return b ? b->b.read_bgra_one(stream, dst, dst_stride) : MOBI_ERR_ARG; }
@@ -695,5 +812,13 @@ int mobi_batch_get_stats(const mobi_batch_t* b, mobi_batch_stats* st) {
     return MOBI_OK;
 }
 void mobi_batch_clear_stats(mobi_batch_t* b) { if (b) b->b.clear_stats(); }
+int mobi_batch_set_kernel_timing(mobi_batch_t* b, int enabled) {
+    if (!b) return MOBI_ERR_ARG;
+    b->b.set_timing(enabled != 0);
+    return MOBI_OK;
+}
+int mobi_batch_get_kernel_times(mobi_batch_t* b, double* inter_ms, uint64_t* inter_launches, double* intra_ms, uint64_t* intra_launches) {
+    return b ? b->b.kernel_times(inter_ms, inter_launches, intra_ms, intra_launches) : MOBI_ERR_ARG;
+}
 
 }  // extern "C"

@@ -355,7 +355,7 @@ struct mobi_synth {
     static int med3(int a, int b, int c) { return std::max(std::min(a, b), std::min(std::max(a, b), c)); }
 
     int next_frame(uint8_t* out, int cap, int* is_key) {
-        bool key = frame_idx == 0 || (P.gop > 0 && frame_idx % P.gop == 0);
+        bool key = frame_idx == 0 || (P.gop > 0 && (frame_idx + P.gop_phase) % P.gop == 0);
         std::memset(&st, 0, sizeof st);
         bw = BitW();
         if (key) {
@@ -426,6 +426,7 @@ mobi_synth_t* mobi_synth_create(const mobi_synth_params* p) {
     s->P = *p;
     s->P.quant = std::max(12, std::min(46, p->quant));
     s->P.mv_range = std::max(0, std::min(32, p->mv_range));
+    if (s->P.gop_phase < 0) s->P.gop_phase = 0;
     s->rng.s = p->seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     s->S = p->width <= 256 ? 256 : p->width <= 512 ? 512 : 1024;
     s->mbw = (int)p->width / 16; s->mbh = (int)p->height / 16;

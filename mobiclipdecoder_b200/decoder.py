@@ -229,6 +229,29 @@ class MobiBatch:
         self._check(rc)
         return list(self._offs), list(self._status)
 
+    OUT_I420, OUT_BGRA = 1, 2
+
+    def submit(self, frames, offsets=None, fmt=1):
+        """Pipelined decode (mobi_batch_submit): returns at once; at most two results may be outstanding."""
+        self._marshal(frames, offsets)
+        self._check(self._lib.mobi_batch_submit(self._h, self._ptrs, self._lens, self._offs, self._status, fmt))
+        return list(self._offs), list(self._status)
+
+    def fetch(self, out=None, copy=True):
+        """Oldest outstanding result as uint8 [n_streams, bytes per stream].  copy=False returns a view of the
+        library's pinned buffer, valid until the second submit() from now."""
+        view, nbytes = C.c_void_p(), C.c_size_t()
+        if copy and out is None:
+            self._check(self._lib.mobi_batch_fetch(self._h, None, C.byref(view), C.byref(nbytes)))
+            a = np.ctypeslib.as_array(C.cast(view, C.POINTER(C.c_uint8)), shape=(nbytes.value,))
+            return a.reshape(self.n_streams, -1).copy()
+        if copy:
+            self._check(self._lib.mobi_batch_fetch(self._h, out.ctypes.data_as(C.c_void_p), None, None))
+            return out
+        self._check(self._lib.mobi_batch_fetch(self._h, None, C.byref(view), C.byref(nbytes)))
+        a = np.ctypeslib.as_array(C.cast(view, C.POINTER(C.c_uint8)), shape=(nbytes.value,))
+        return a.reshape(self.n_streams, -1)
+
     def stage(self, frames, offsets=None):
         self._marshal(frames, offsets)
         self._check(self._lib.mobi_batch_stage(self._h, self._ptrs, self._lens, self._offs))
@@ -289,6 +312,15 @@ class MobiBatch:
 
     def clear_stats(self):
         self._lib.mobi_batch_clear_stats(self._h)
+
+    def set_kernel_timing(self, on):
+        self._check(self._lib.mobi_batch_set_kernel_timing(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{'inter_ms', 'inter_launches', 'intra_ms', 'intra_launches'} since the last call (synchronises)."""
+        a, b, c, d = C.c_double(), C.c_uint64(), C.c_double(), C.c_uint64()
+        self._check(self._lib.mobi_batch_get_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {'inter_ms': a.value, 'inter_launches': b.value, 'intra_ms': c.value, 'intra_launches': d.value}
 
     def close(self):
         if getattr(self, '_h', None):
