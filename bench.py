@@ -284,18 +284,16 @@ def main():
     kt = batch.kernel_times()
     batch.set_kernel_timing(False)
     inter_bytes = (768 + 16) * d['inter_mbs'] + 8 * d['parts'] + 4 * d['inter_coefs']
-    intra_bytes = (384 + 16) * d['intra_mbs'] + 4 * d['ops'] + 4 * (d['coefs'] - d['inter_coefs'])
+    intra_bytes = (384 + 32) * d['intra_mbs'] + 4 * d['ops'] + 4 * (d['coefs'] - d['inter_coefs'])
     n_il = max(1, kt['inter_launches'])
     inter_ms = kt['inter_ms'] / n_il
     achieved = (inter_bytes / n_il) / (inter_ms * 1e-3) / 1e9 if inter_ms > 0 else 0.0
     roofline = {'bound': 'hbm', 'kernel': 'k_inter', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': NCU_TRAFFIC.get('k_inter'), 'algorithmic_bytes_per_launch': inter_bytes / n_il, 'launch_ms': inter_ms,
                 'launches_timed': kt['inter_launches'], 'peak_source': peak_src,
-                'share_of_step': kt['inter_ms'] / max(1e-9, kt['inter_ms'] + kt['intra_ms']),
-                'other_kernels': {'k_intra': {'launch_ms': kt['intra_ms'] / max(1, kt['intra_launches']), 'launches_timed': kt['intra_launches'],
-                                              'algorithmic_bytes_per_launch': intra_bytes / max(1, kt['intra_launches']),
-                                              'achieved': (intra_bytes / max(1e-9, kt['intra_ms'] * 1e-3)) / 1e9 if kt['intra_ms'] > 0 else 0.0,
-                                              'traffic': NCU_TRAFFIC.get('k_intra')}}}
+                'step_ms_by_kernel': {'k_inter': kt['inter_ms'] / K, 'k_intra_p_pictures': kt['intra_ms'] / K,
+                                      'k_intra_i_pictures_side_stream': kt['key_ms'] / K},
+                'intra_algorithmic_bytes_per_step': intra_bytes / K}
 
     # ---- e2e leg: host bytes -> parse -> H2D -> reconstruct -> BGRA -> D2H (pinned) -----------------------
     e2e = None

@@ -57,8 +57,10 @@ typedef struct mobi_frame_hdr {
 
 /* One per macroblock, raster order. */
 typedef struct mobi_mb {
-    uint32_t info;         /* bits 0-1 kind: 0 inter, 1 intra; bits 2-8 n_sub (partitions or intra ops, <= 64);
-                              bits 9-17 n_coefs (<= 384); bits 18-23 mask of 8x8 blocks holding >= 1 coefficient */
+    uint32_t info;         /* bits 0-1 kind: 0 inter, 1 intra; bits 2-8 n_sub (partitions <= 64, or intra ops <= 27);
+                              bits 9-17 n_coefs (<= 384); bits 18-23 mask of 8x8 blocks holding >= 1 coefficient;
+                              bits 24-27 (intra) neighbouring macroblocks whose pixels the predictors read:
+                              1 left (m-1), 2 top-left (m-mbw-1), 4 top (m-mbw), 8 top-right (m-mbw+1) */
     uint32_t first_sub;    /* index of the first mobi_part (inter) or mobi_op (intra) */
     uint32_t first_coef;   /* index of the first mobi_coef */
     uint32_t intra_rank;   /* intra MBs: position in the frame's intra list; inter: 0 */
@@ -198,7 +200,9 @@ int mobi_batch_get_stats(const mobi_batch_t* b, mobi_batch_stats* st);
  * by CUDA events on the batch's stream.  mobi_batch_get_kernel_times synchronises, returns the summed durations
  * (milliseconds) and launch counts since the last call, and clears them. */
 int mobi_batch_set_kernel_timing(mobi_batch_t* b, int enabled);
-int mobi_batch_get_kernel_times(mobi_batch_t* b, double* inter_ms, uint64_t* inter_launches, double* intra_ms, uint64_t* intra_launches);
+/* index 0: k_inter; 1: k_intra over the intra macroblocks of P-pictures; 2: k_intra over I-pictures (runs on a second
+ * CUDA stream, concurrently with the other two) */
+int mobi_batch_get_kernel_times(mobi_batch_t* b, double ms[3], uint64_t launches[3]);
 void mobi_batch_clear_stats(mobi_batch_t* b);
 
 int mobicuda_abi_version(void);

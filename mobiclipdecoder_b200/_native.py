@@ -71,7 +71,7 @@ MOBICUDA_EXPORTS = {
     'mobi_batch_get_stats': (C.c_int, [C.c_void_p, C.POINTER(BatchStats)]),
     'mobi_batch_clear_stats': (None, [C.c_void_p]),
     'mobi_batch_set_kernel_timing': (C.c_int, [C.c_void_p, C.c_int]),
-    'mobi_batch_get_kernel_times': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    'mobi_batch_get_kernel_times': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
 
 

@@ -301,33 +301,39 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DevJob* __rest
 // ------------------------------------------------------------------------------------------------
 // intra macroblocks
 // ------------------------------------------------------------------------------------------------
-// Shared tiles: luma rows y-1..y+15, columns x-4..x+27 (column x at index 4, so x-1 = 3 and the
-// top-right / right-hand run x+16..x+20 = 20..24); chroma rows c-1..c+7, column c at index 4.
+// Per-warp shared state.  Pixel tiles: luma rows y-1..y+15, columns x-4..x+27 (column x at index 4, so x-1 = 3 and
+// the top-right / right-hand run x+16..x+20 = 20..24); chroma rows c-1..c+7, column c at index 4.
 struct IntraSmem {
     uint8_t y[17][32];
     uint8_t c[2][9][16];
-    int32_t coef[64];
+    int32_t coef[64];      // one transform block
+    uint32_t qtab[80];     // the picture's dequantisation words (MD:3897-3912)
+    uint32_t cf[384];      // the macroblock's coefficient records
 };
 
-__device__ __forceinline__ uint32_t nb_luma(const DevJob& J, const Geom& g, int flat, uint32_t m) {
+// Is the 4-byte word at flat luma address `flat` (a) inside the array, (b) inside the visible picture, (c) part of a
+// macroblock that precedes m in decode order?  Otherwise the reference reads 0 there: fresh planes (MD:107-108).
+// MB and picture edges are multiples of 16, so the answer is the same for all four bytes of an aligned word.
+__device__ __forceinline__ uint32_t nb_luma4(const DevJob& J, const Geom& g, int flat, uint32_t m) {
     if (flat < 0 || flat >= g.S * g.H) return 0;
     const int row = flat >> g.log2S, col = flat & (g.S - 1);
-    if (col >= g.W) return 0;                                       // stride padding: never written
-    if ((uint32_t)((row >> 4) * g.mbw + (col >> 4)) >= m) return 0; // later in decode order: still zero in the reference
-    return __ldcg(J.dst + flat);
+    if (col >= g.W) return 0;
+    if ((uint32_t)((row >> 4) * g.mbw + (col >> 4)) >= m) return 0;
+    return __ldcg(reinterpret_cast<const uint32_t*>(J.dst + flat));
 }
-__device__ __forceinline__ uint32_t nb_chroma(const DevJob& J, const Geom& g, int flat, uint32_t m) {
+__device__ __forceinline__ uint32_t nb_chroma4(const DevJob& J, const Geom& g, int flat, uint32_t m) {
     if (flat < 0 || flat >= (g.S * g.H >> 1)) return 0;
     const int row = flat >> g.log2S, col = flat & (g.S - 1);
     const int pc = col < (g.S >> 1) ? col : col - (g.S >> 1);
     if (pc >= (g.W >> 1)) return 0;
     if ((uint32_t)((row >> 3) * g.mbw + (pc >> 3)) >= m) return 0;
-    return __ldcg(J.dst + (size_t)g.S * g.H + flat);
+    return __ldcg(reinterpret_cast<const uint32_t*>(J.dst + (size_t)g.S * g.H + flat));
 }
 
 // Value of pixel (x,y) of an NxN block under predictor `mode` (0,1,4..8: MD:1890-2472 / 2475-2769 closed forms).
-// t points at the block's top-left pixel inside a shared tile with row pitch ts.
-__device__ __forceinline__ int dir_px(const uint8_t* t, int ts, int mode, int N, int x, int y) {
+// t points at the block's top-left pixel inside a shared tile with row pitch ts.  All reads are outside the block.
+template <int N>
+__device__ __forceinline__ int dir_px(const uint8_t* t, int ts, int mode, int x, int y) {
 #define TT(k) ((int)t[-ts + (k)])
 #define LL(k) ((int)t[(k) * ts - 1])
     switch (mode) {
@@ -366,7 +372,8 @@ __device__ __forceinline__ int dir_px(const uint8_t* t, int ts, int mode, int N,
 }
 // Unclipped plane-predictor value (sub_1167BC MD:3017 for N=16, sub_116CCC MD:3168 for 8, sub_117E98 MD:3253 for 4),
 // the reference's running sums written in closed form (all arithmetic int32, wrap-around like C#).
-__device__ __forceinline__ int plane_val(const uint8_t* t, int ts, int N, int delta, int x, int y) {
+template <int N>
+__device__ __forceinline__ int plane_val(const uint8_t* t, int ts, int delta, int x, int y) {
     const int l = t[(N - 1) * ts - 1], tt = t[-ts + N - 1], T = t[-ts + x], L = t[y * ts - 1];
     const int m = ((l + tt + 1) >> 1) + delta * 2;
     if (N == 16) {
@@ -375,77 +382,95 @@ __device__ __forceinline__ int plane_val(const uint8_t* t, int ts, int N, int de
         const int step = (tt * 8 + (y + 1) * gy) - L * 8 + 1, run = L * 64 + (x + 1) * (step >> 1);
         return (A + run + 64) >> 7;
     }
-    const int sh = N == 8 ? 3 : 2;
+    constexpr int sh = N == 8 ? 3 : 2;
     const int gx = m - l, gy = m - tt;
     const int Bc = ((l << sh) + (x + 1) * gx) - (T << sh), A = (T << (2 * sh)) + (y + 1) * Bc;
     const int step = ((tt << sh) + (y + 1) * gy) - (L << sh), run = (L << (2 * sh)) + (x + 1) * step;
     return N == 8 ? (A + run + 64) >> 7 : (A + run + 16) >> 5;
 }
-// The reference ORs four unclipped values into one u32 (MD:3064-3074): byte k also receives the
-// overflow of bytes < k of the same word.
-__device__ __forceinline__ uint8_t plane_px(const uint8_t* t, int ts, int N, int delta, int x, int y) {
-    uint32_t acc = 0;
-    for (int xx = x & ~3; xx <= x; xx++) acc |= (uint32_t)plane_val(t, ts, N, delta, xx, y) >> (8 * (x - xx));
-    return (uint8_t)acc;
-}
 
-// One intra op: predict an NxN block inside a shared tile (t = its top-left pixel).
-__device__ void intra_predict(uint8_t* t, int ts, int mode, int N, int delta, bool left_av, bool top_av, int lane) {
-    const int npx = N * N;
-    uint8_t out[8];
-    int cnt = 0;
+// One intra op: predict an NxN block inside a shared tile (t = its top-left pixel, 4-byte aligned).  Predictors read
+// only pixels outside the block, so values are computed and stored without an intermediate barrier.
+template <int N>
+__device__ __forceinline__ void intra_predict(uint8_t* t, int ts, int mode, int delta, bool left_av, bool top_av, int lane) {
+    constexpr int WORDS = N * N / 4, WPR = N / 4;  // 4-pixel words in the block / per row
     if (mode == 3) {  // DC by flat-offset availability (MD:1920-2022, 2501-2580)
-        int sum = 0;
-        if (top_av) for (int k = 0; k < N; k++) sum += t[-ts + k];
-        if (left_av) for (int k = 0; k < N; k++) sum += t[k * ts - 1];
-        int dc;
+        unsigned sum = 0;
+        if (top_av) {
+#pragma unroll
+            for (int k = 0; k < N; k += 4) sum = __dp4a(*reinterpret_cast<const uint32_t*>(t - ts + k), 0x01010101u, sum);
+        }
+        if (left_av) {
+#pragma unroll
+            for (int k = 0; k < N; k++) sum += t[k * ts - 1];
+        }
+        unsigned dc;
         if (top_av && left_av) dc = (sum + N) / (2 * N);
         else if (top_av || left_av) dc = (sum + N / 2) / N;
         else dc = 0x80;
-        for (int i = lane; i < npx; i += 32) out[cnt++] = (uint8_t)dc;
+        const uint32_t w = (dc & 255u) * 0x01010101u;
+        for (int i = lane; i < WORDS; i += 32) *reinterpret_cast<uint32_t*>(t + (i / WPR) * ts + (i % WPR) * 4) = w;
     } else if (mode == 2) {
-        for (int i = lane; i < npx; i += 32) out[cnt++] = plane_px(t, ts, N, delta, i % N, i / N);
+        // the reference ORs four unclipped values into one u32 (MD:3064-3074, 3212-3219, 3314-3321): a value outside
+        // 0..255 bleeds into the bytes above it, and the top byte's overflow is lost
+        for (int i = lane; i < WORDS; i += 32) {
+            const int y = i / WPR, x = (i % WPR) * 4;
+            const uint32_t w = (uint32_t)plane_val<N>(t, ts, delta, x, y) | (uint32_t)plane_val<N>(t, ts, delta, x + 1, y) << 8 |
+                               (uint32_t)plane_val<N>(t, ts, delta, x + 2, y) << 16 | (uint32_t)plane_val<N>(t, ts, delta, x + 3, y) << 24;
+            *reinterpret_cast<uint32_t*>(t + y * ts + x) = w;
+        }
     } else {
-        for (int i = lane; i < npx; i += 32) out[cnt++] = (uint8_t)dir_px(t, ts, mode, N, i % N, i / N);
+        for (int i = lane; i < WORDS; i += 32) {
+            const int y = i / WPR, x = (i % WPR) * 4;
+            const uint32_t w = (uint32_t)dir_px<N>(t, ts, mode, x, y) | (uint32_t)dir_px<N>(t, ts, mode, x + 1, y) << 8 |
+                               (uint32_t)dir_px<N>(t, ts, mode, x + 2, y) << 16 | (uint32_t)dir_px<N>(t, ts, mode, x + 3, y) << 24;
+            *reinterpret_cast<uint32_t*>(t + y * ts + x) = w;
+        }
     }
-    __syncwarp();
-    cnt = 0;
-    for (int i = lane; i < npx; i += 32) t[(i / N) * ts + (i % N)] = out[cnt++];
     __syncwarp();
 }
 
-// Residual of one transform unit added onto the tile (loc_116540 MD:2931 / sub_1166E8 MD:2958).
-__device__ void intra_residual(uint8_t* t, int ts, int N, int32_t* cb, const uint32_t* __restrict__ qtab,
-                               const uint32_t* __restrict__ coefs, uint32_t& cursor, uint32_t end, int lane) {
+// Residual of one transform unit added onto the tile (loc_116540 MD:2931 / sub_1166E8 MD:2958).  The unit's
+// coefficient records start at cf[cursor] and end at the record flagged "last".
+template <int N>
+__device__ __forceinline__ void intra_residual(uint8_t* t, int ts, int32_t* cb, const uint32_t* qtab, const uint32_t* cf,
+                                               uint32_t& cursor, uint32_t end, int lane) {
     for (int i = lane; i < N * N; i += 32) cb[i] = 0;
     __syncwarp();
-    for (;;) {  // the unit's coefficients end at the record flagged "last"
+    for (;;) {
         const uint32_t j = cursor + lane;
-        const uint32_t c = j < end ? __ldg(coefs + j) : 0u;
+        const uint32_t c = j < end ? cf[j] : 0u;
         const uint32_t lastmask = __ballot_sync(0xffffffffu, j < end && ((c >> 30) & 1u));
         const int n = lastmask ? __ffs(lastmask) : 32;
         if (lane < n && j < end) {
             const uint32_t pos = (c >> 16) & 63u;
-            const uint32_t w = __ldg(qtab + (N == 8 ? pos : 64u + pos));
+            const uint32_t w = qtab[N == 8 ? pos : 64u + (pos & 15u)];
             cb[w & (uint32_t)(N * N - 1)] = (int)(w >> 8) * (int)(int16_t)(c & 0xFFFFu);
         }
         cursor += n;
         if (lastmask || cursor >= end) break;
     }
     __syncwarp();
-    int32_t in[8], v[8];
+    int32_t in[N], v[N];
     if (lane < N) {
+#pragma unroll
         for (int k = 0; k < N; k++) in[k] = cb[N * lane + k];
         if (lane == 0) in[0] += 32;
-        if (N == 8) bfly8(in, v); else bfly4(in, v);
+        if constexpr (N == 8) bfly8(in, v); else bfly4(in, v);
     }
     __syncwarp();
-    if (lane < N) for (int k = 0; k < N; k++) cb[N * k + lane] = v[k];
+    if (lane < N) {
+#pragma unroll
+        for (int k = 0; k < N; k++) cb[N * k + lane] = v[k];
+    }
     __syncwarp();
     if (lane < N) {
+#pragma unroll
         for (int k = 0; k < N; k++) in[k] = cb[N * lane + k];
-        if (N == 8) bfly8(in, v); else bfly4(in, v);
-        for (int k = 0; k < N; k++) t[lane * ts + k] = (uint8_t)clip255((int)t[lane * ts + k] + (v[k] >> 6));
+        if constexpr (N == 8) bfly8(in, v); else bfly4(in, v);
+        uint32_t* row = reinterpret_cast<uint32_t*>(t + lane * ts);
+#pragma unroll
+        for (int k = 0; k < N; k += 4) row[k >> 2] = addclip4(row[k >> 2], v + k);
     }
     __syncwarp();
 }
@@ -461,63 +486,72 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32) k_intra(const DevJob* __rest
         if (lane == 0) t = atomicAdd(ticket, 1u) - ticket_base;
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_work) break;
-        const IntraWork wk = work[t];
-        const DevJob& J = jobs[wk.job];
-        const uint32_t m = __ldg(J.intra + wk.rank);
-        const uint4 d = __ldg(reinterpret_cast<const uint4*>(J.mbs + m));
-        const int n_ops = (int)((d.x >> 2) & 127u);
-        const uint32_t coef_end = d.z + ((d.x >> 9) & 511u);
-        uint32_t cursor = d.z;
+        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(work + t));
+        const uint2 w1 = __ldg(reinterpret_cast<const uint2*>(work + t) + 2);
+        const DevJob& J = jobs[w0.x];
+        const uint32_t m = w0.y, info = w0.z;
+        const int n_ops = (int)((info >> 2) & 127u), n_coef = (int)((info >> 9) & 511u);
         const int mbx = (int)(m % (uint32_t)g.mbw), mby = (int)(m / (uint32_t)g.mbw);
         const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
 
-        // wait for the intra neighbours this MB may read: left, top-left, top, top-right in raster
-        // numbering (which also covers the flat-address wrap at the picture edges when W == Stride)
-        if (lane < 4) {
+        // ---- everything that does not depend on neighbouring macroblocks is fetched before the wait ----
+        const uint32_t myop = lane < n_ops ? __ldg(J.ops + w0.w + lane) : 0u;
+        {
+            const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs) + w1.x;
+            for (int i = lane; i < n_coef; i += 32) sm.cf[i] = __ldg(cf + i);
+            const uint32_t* qt = J.hdr->qtab;
+            for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
+            uint4* z = reinterpret_cast<uint4*>(&sm.y[0][0]);  // y and c tiles are contiguous: 832 B = 52 x 16
+            for (int i = lane; i < 52; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+        }
+
+        // ---- wait for the intra neighbours whose pixels this macroblock's predictors read (host-computed mask) ----
+        if (lane < 4 && ((w1.y >> lane) & 1u)) {
             const int nb = lane == 0 ? (int)m - 1 : (int)m - g.mbw - 2 + lane;
-            if (nb >= 0 && nb < (int)m && (__ldg(&J.mbs[nb].info) & 3u) == 1u) {
-                volatile uint32_t* f = J.flags + nb;
-                while (*f != stamp) __nanosleep(32);
-            }
+            volatile uint32_t* f = J.flags + nb;
+            while (*f != stamp) __nanosleep(20);
         }
         __syncwarp();
         __threadfence();
 
-        // stage neighbourhoods; the MB's own pixels start at zero like the reference's fresh planes
-        for (int r = 0; r < 17; r++) {
-            const int c = lane;
-            uint32_t v = 0;
-            if ((r == 0 && c >= 3 && c <= 24) || (r > 0 && (c == 3 || (c >= 20 && c <= 24))))
-                v = nb_luma(J, g, yoff + (r - 1) * S + (c - 4), m);
-            sm.y[r][c] = (uint8_t)v;
-        }
-        for (int i = lane; i < 2 * 9 * 16; i += 32) {
-            const int p = i / 144, r = (i % 144) / 16, c = i % 16;
-            uint32_t v = 0;
-            if ((r == 0 && c >= 3 && c <= 11) || (r > 0 && c == 3))
-                v = nb_chroma(J, g, coff + (p ? (S >> 1) : 0) + (r - 1) * S + (c - 4), m);
-            sm.c[p][r][c] = (uint8_t)v;
+        // ---- stage the neighbourhood: one round of independent aligned word loads ----
+        // luma: 7 words of row y-1 (columns x-4..x+23), then columns x-4..x-1 of rows y..y+15; when the picture is as
+        // wide as the stride the columns right of the last macroblock wrap onto real pixels of the next row, so the
+        // right-hand run x+16..x+23 of rows y..y+15 is staged too (otherwise it is zero: not yet decoded / padding).
+        const bool wrap = g.W == S && mbx == g.mbw - 1;
+        for (int i = lane; i < 45 + (wrap ? 32 : 0); i += 32) {
+            if (i < 7) *reinterpret_cast<uint32_t*>(&sm.y[0][4 * i]) = nb_luma4(J, g, yoff - S - 4 + 4 * i, m);
+            else if (i < 23) *reinterpret_cast<uint32_t*>(&sm.y[i - 6][0]) = nb_luma4(J, g, yoff + (i - 7) * S - 4, m);
+            else if (i < 45) {
+                const int k = i - 23, p = k / 11, q = k % 11, base = coff + (p ? (S >> 1) : 0);
+                if (q < 3) *reinterpret_cast<uint32_t*>(&sm.c[p][0][4 * q]) = nb_chroma4(J, g, base - S - 4 + 4 * q, m);
+                else *reinterpret_cast<uint32_t*>(&sm.c[p][q - 2][0]) = nb_chroma4(J, g, base + (q - 3) * S - 4, m);
+            } else {
+                const int k = i - 45, r = k >> 1, h = k & 1;
+                *reinterpret_cast<uint32_t*>(&sm.y[1 + r][20 + 4 * h]) = nb_luma4(J, g, yoff + r * S + 16 + 4 * h, m);
+            }
         }
         __syncwarp();
 
-        const uint32_t* qtab = J.hdr->qtab;
-        const uint32_t* coefs = reinterpret_cast<const uint32_t*>(J.coefs);
+        uint32_t cursor = 0;
         for (int k = 0; k < n_ops; k++) {
-            const uint32_t op = __ldg(J.ops + d.y + k);
+            const uint32_t op = __shfl_sync(0xffffffffu, myop, k);
             const int mode = (int)(op & 31u), plane = (int)((op >> 6) & 3u), x4 = (int)((op >> 8) & 3u), y4 = (int)((op >> 10) & 3u);
             const bool res = (op >> 5) & 1u;
             const int delta = (int)(int16_t)(op >> 16);
             uint8_t* tp; int ts, off;
             if (plane == 0) { ts = 32; tp = &sm.y[1 + y4 * 4][4 + x4 * 4]; off = yoff + y4 * 4 * S + x4 * 4; }
             else { ts = 16; tp = &sm.c[plane - 1][1 + y4 * 4][4 + x4 * 4]; off = coff + (plane == 2 ? (S >> 1) : 0) + y4 * 4 * S + x4 * 4; }
-            int N, pm = mode;
-            if (mode == 20) { N = 16; pm = 2; } else if (mode >= 10) { N = 4; pm = mode - 10; } else N = 8;
-            if (pm != 9) {
-                const bool left_av = ((off - (plane == 2 ? (S >> 1) : 0)) & (S - 1)) != 0;  // MD:1923, VOffsetfix MD:1885
-                const bool top_av = off >= S;                                               // MD:1924
-                intra_predict(tp, ts, pm, N, delta, left_av, top_av, lane);
+            const bool left_av = ((off - (plane == 2 ? (S >> 1) : 0)) & (S - 1)) != 0;  // MD:1923, VOffsetfix MD:1885
+            const bool top_av = off >= S;                                               // MD:1924
+            if (mode == 20) intra_predict<16>(tp, ts, 2, delta, left_av, top_av, lane);
+            else if (mode >= 10) {
+                if (mode != 19) intra_predict<4>(tp, ts, mode - 10, delta, left_av, top_av, lane);
+                if (res) intra_residual<4>(tp, ts, sm.coef, sm.qtab, sm.cf, cursor, (uint32_t)n_coef, lane);
+            } else {
+                if (mode != 9) intra_predict<8>(tp, ts, mode, delta, left_av, top_av, lane);
+                if (res) intra_residual<8>(tp, ts, sm.coef, sm.qtab, sm.cf, cursor, (uint32_t)n_coef, lane);
             }
-            if (res) intra_residual(tp, ts, N == 16 ? 8 : N, sm.coef, qtab, coefs, cursor, coef_end, lane);
         }
 
         // write the macroblock out
@@ -605,12 +639,14 @@ cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, cudaStream_t st
 }
 
 cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_work, uint32_t* ticket, uint32_t ticket_base,
-                         uint32_t stamp, Geom g, int sm_count, cudaStream_t st, uint32_t* warps_launched) {
+                         uint32_t stamp, Geom g, uint32_t max_warps, cudaStream_t st, uint32_t* warps_launched) {
     *warps_launched = 0;
     if (n_work == 0) return cudaSuccess;
-    // every warp that holds a ticket must be resident: size the grid to what fits, never more
+    // Tickets are handed out in dependency-depth order, so a warp only ever waits for tickets drawn before its own,
+    // which are held by warps that are already running: any grid size makes progress.
     unsigned blocks = (unsigned)((n_work + INTRA_WARPS - 1) / INTRA_WARPS);
-    unsigned cap = (unsigned)sm_count * 8u;
+    unsigned cap = (max_warps + INTRA_WARPS - 1) / INTRA_WARPS;
+    if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
     k_intra<<<blocks, INTRA_WARPS * 32, 0, st>>>(jobs, work, n_work, ticket, ticket_base, stamp, g);
     *warps_launched = blocks * INTRA_WARPS;

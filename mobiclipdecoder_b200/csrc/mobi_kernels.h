@@ -21,7 +21,10 @@ struct alignas(16) DevJob {
     uint32_t pad[2];
 };
 
-struct IntraWork { uint32_t job, rank; };
+// One intra macroblock to reconstruct: its descriptor travels with the work item so that the warp needs no dependent
+// loads to find it.  wait: bit 0 left (m-1), 1 top-left (m-mbw-1), 2 top (m-mbw), 3 top-right (m-mbw+1): neighbours that
+// are intra macroblocks of the same picture and whose pixels the predictors read -- their completion stamps are awaited.
+struct alignas(16) IntraWork { uint32_t job, mb, info, first_op, first_coef, wait, pad[2]; };
 
 struct Geom {
     int W, H, S, log2S, mbw, mbh, version;
@@ -29,12 +32,12 @@ struct Geom {
 
 // Inter macroblocks of every job: MC from the ring + dequant/IDCT/add/clip.  One warp per MB.
 cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, cudaStream_t st);
-// Intra macroblocks (I-frames and intra MBs of P-frames) in decode-order wavefront.  One warp per MB,
-// work handed out through an atomic ticket so that a waiting warp's dependencies are always running.
+// Intra macroblocks (I-frames and intra MBs of P-frames) as a dependency wavefront.  One warp per MB; work is handed
+// out through an atomic ticket in dependency-depth order so that a waiting warp's dependencies are always running.
 // *warps_launched receives the number of warps started: each draws exactly one ticket past n_work, so the
 // next launch's ticket_base is ticket_base + n_work + *warps_launched.
 cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_work, uint32_t* ticket, uint32_t ticket_base,
-                         uint32_t stamp, Geom g, int sm_count, cudaStream_t st, uint32_t* warps_launched);
+                         uint32_t stamp, Geom g, uint32_t max_warps, cudaStream_t st, uint32_t* warps_launched);
 // Y/UV planes of n pictures -> BGRA (MD:260-323). srcs = device array of luma plane pointers; picture i goes to
 // dst + i*dst_picture_bytes with dst_pitch bytes per row.
 cudaError_t launch_bgra(const uint8_t* const* srcs, int n, uint8_t* dst, int dst_pitch, size_t dst_picture_bytes, Geom g, cudaStream_t st);

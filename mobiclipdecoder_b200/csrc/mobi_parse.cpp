@@ -78,6 +78,8 @@ struct FrameParse {
     int32_t mvpx = 0, mvpy = 0;
     int S, W, H;
     uint32_t max_ref = 0;
+    uint32_t cur_deps = 0;
+    int cur_mbx = 0, cur_mby = 0;
 
     FrameParse(Parser& p, ParsedFrame& o) : P(p), out(o), S(p.S_), W((int)p.W_), H((int)p.H_) {}
 
@@ -183,9 +185,47 @@ struct FrameParse {
         if (plane == 0) return mboff + y4 * 4 * S + x4 * 4;
         return mboff / 2 + (plane == 2 ? S / 2 : 0) + y4 * 4 * S + x4 * 4;
     }
+    // Which neighbouring macroblocks does this predictor read?  bit 0 left (m-1), 1 top-left (m-mbw-1), 2 top (m-mbw),
+    // 3 top-right (m-mbw+1), in raster numbering -- which is also what the reference's flat addressing resolves to at
+    // the picture edges: the "left" of column 0 is the last byte of the previous row, i.e. the previous MB row's last
+    // macroblock when Width == Stride and zero padding otherwise (SURVEY.md 8a hazard 2).  Footprints: SURVEY.md App. C.
+    void note_deps(uint32_t mode, int plane, int x4, int y4, int off) {
+        int N = 8, pm = (int)mode;
+        if (mode == 20) { N = 16; pm = 2; } else if (mode >= 10) { N = 4; pm = (int)mode - 10; }
+        if (pm == 9) return;
+        bool top = false, left = false, tl = false;
+        int ext = 0;  // pixels read beyond the block's right edge in the row above
+        switch (pm) {
+        case 0: top = true; break;
+        case 1: case 4: left = true; break;
+        case 2: top = left = true; break;
+        case 3: {
+            const int po = plane == 2 ? off - S / 2 : off;
+            left = (po % S) != 0; top = off >= S;   // MD:1923-1924
+            break; }
+        case 5: case 6: case 7: top = left = tl = true; break;
+        case 8: top = true; ext = N == 8 ? 5 : 4; break;   // T0..12 / two top words (MD:2371-2466, 2737-2746)
+        }
+        const int cells = plane == 0 ? 4 : 2;          // macroblock width in 4-pixel cells on this plane
+        const int xe = x4 + N / 4;                     // first cell right of the block
+        uint32_t d = 0;
+        if (top && y4 == 0) d |= 4u;
+        if (left && x4 == 0) d |= 1u;
+        if (tl) d |= (x4 == 0 && y4 == 0) ? 2u : (x4 == 0 ? 1u : (y4 == 0 ? 4u : 0u));
+        const bool beyond = ext && xe * 4 + ext > cells * 4;  // the row above is read past the macroblock's right edge
+        if (beyond && y4 == 0) d |= 8u;
+        if (cur_mbx == 0 && W != S) d &= ~3u;              // reads land in the zero padding of the previous row
+        if (cur_mbx == P.mbw_ - 1 && W != S) d &= ~8u;
+        if (cur_mby == 0) d &= ~14u;
+        // Width == Stride, last column, block below the MB's top edge: "right of the macroblock" wraps onto the next
+        // pixel row, columns 0.., which belong to the first macroblock of this MB row (index m-mbw+1), already decoded
+        if (beyond && y4 > 0 && cur_mbx == P.mbw_ - 1 && W == S && P.mbw_ > 1) d |= 8u;
+        cur_deps |= d;
+    }
     void emit_op(uint32_t mode, bool res, int plane, int x4, int y4, int delta, int mboff) {
         if (delta < -32768 || delta > 32767) fail(MOBI_ERR_BITSTREAM, "plane-predictor delta outside 16 bits");
         check_intra_reads(mode, plane_off(plane, mboff, x4, y4));
+        note_deps(mode, plane, x4, y4, plane_off(plane, mboff, x4, y4));
         if ((mode == 9 || mode == 19) && !res) return;
         out.ops.push_back((mode & 31) | (res ? 32u : 0u) | (uint32_t)plane << 6 | (uint32_t)x4 << 8 | (uint32_t)y4 << 10 | (uint32_t)(uint16_t)(int16_t)delta << 16);
     }
@@ -283,9 +323,11 @@ struct FrameParse {
     void intra_mb(bool sub, int mboff) {
         mobi_mb mb;
         uint32_t first_op = (uint32_t)out.ops.size(), first_coef = (uint32_t)out.coefs.size(), mask = 0;
+        cur_deps = 0;
+        cur_mbx = (mboff % S) / 16; cur_mby = (mboff / S) / 16;
         if (sub) intra_sub(mboff, mask); else intra_full(mboff, mask);
         uint32_t nops = (uint32_t)out.ops.size() - first_op, nco = (uint32_t)out.coefs.size() - first_coef;
-        mb.info = 1u | nops << 2 | nco << 9 | mask << 18;
+        mb.info = 1u | nops << 2 | nco << 9 | mask << 18 | cur_deps << 24;
         mb.first_sub = first_op; mb.first_coef = first_coef; mb.intra_rank = (uint32_t)out.intra.size();
         out.intra.push_back((uint32_t)out.mbs.size());
         out.mbs.push_back(mb);

@@ -103,8 +103,9 @@ struct Arena {
 struct StepLayout {
     size_t bytes = 0;
     size_t jobs_off = 0, work_off = 0;
-    int n_jobs = 0, n_inter_jobs = 0;
-    uint32_t n_work = 0;
+    int n_jobs = 0, n_inter_jobs = 0, n_key_jobs = 0;
+    uint32_t n_work = 0;      // all intra macroblocks; the list holds those of P-pictures first, then those of I-pictures
+    uint32_t n_work_p = 0;    // intra macroblocks inside P-pictures
     std::vector<int> job_stream;  // stream index of each job
     uint64_t mbs = 0, inter_mbs = 0, intra_mbs = 0, parts = 0, coefs = 0, ops = 0, inter_coefs = 0;
 };
@@ -154,7 +155,10 @@ public:
             if (out_h_) cudaFreeHost(out_h_);
             if (ptr_d_) cudaFree(ptr_d_);
             if (ptr_h_) cudaFreeHost(ptr_h_);
-            for (int w = 0; w < 2; w++) for (cudaEvent_t e : ev_[w]) cudaEventDestroy(e);
+            for (int w = 0; w < 3; w++) for (cudaEvent_t e : ev_[w]) cudaEventDestroy(e);
+            if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
+            if (fork_) cudaEventDestroy(fork_);
+            if (join_) cudaEventDestroy(join_);
             for (cudaEvent_t e : ev_free_) cudaEventDestroy(e);
             for (auto& o : slot_) {
                 if (o.h) cudaFreeHost(o.h);
@@ -173,6 +177,9 @@ public:
         if (!ok(cudaGetDeviceProperties(&prop, dev_), "cudaGetDeviceProperties")) return MOBI_ERR_CUDA;
         sm_count_ = prop.multiProcessorCount;
         if (!ok(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return MOBI_ERR_CUDA;
+        if (!ok(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking), "cudaStreamCreate")) return MOBI_ERR_CUDA;
+        if (!ok(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming), "cudaEventCreate")) return MOBI_ERR_CUDA;
+        if (!ok(cudaEventCreateWithFlags(&join_, cudaEventDisableTiming), "cudaEventCreate")) return MOBI_ERR_CUDA;
         if (!ok(cudaMalloc(&ring_, pic_ * RING * (size_t)N_), "cudaMalloc(ring)")) return MOBI_ERR_NOMEM;
         if (!ok(cudaMemsetAsync(ring_, 0, pic_ * RING * (size_t)N_, stream_), "memset(ring)")) return MOBI_ERR_CUDA;
         if (!ok(cudaMalloc(&flags_, sizeof(uint32_t) * n_mb_ * (size_t)N_), "cudaMalloc(flags)")) return MOBI_ERR_NOMEM;
@@ -444,30 +451,28 @@ public:
 
     // ---- per-kernel timing (roofline accounting) ---------------------------------------------------
     void set_timing(bool on) { timing_ = on; }
-    void tick(int which) {
+    void tick(int which, cudaStream_t st) {
         cudaEvent_t e;
         if (ev_free_.empty()) cudaEventCreate(&e); else { e = ev_free_.back(); ev_free_.pop_back(); }
-        cudaEventRecord(e, stream_);
+        cudaEventRecord(e, st);
         ev_[which].push_back(e);
     }
-    int kernel_times(double* inter_ms, uint64_t* inter_n, double* intra_ms, uint64_t* intra_n) {
+    // which: 0 k_inter, 1 k_intra over P-pictures, 2 k_intra over I-pictures (side stream)
+    int kernel_times(double* ms_out, uint64_t* n_out) {
         int rc = sync();
         if (rc != MOBI_OK) return rc;
-        double ms[2] = {0, 0};
-        uint64_t n[2] = {0, 0};
-        for (int w = 0; w < 2; w++) {
+        for (int w = 0; w < 3; w++) {
+            double ms = 0; uint64_t n = 0;
             for (size_t i = 0; i + 1 < ev_[w].size(); i += 2) {
                 float t = 0;
                 cudaEventElapsedTime(&t, ev_[w][i], ev_[w][i + 1]);
-                ms[w] += t; n[w]++;
+                ms += t; n++;
             }
             for (cudaEvent_t e : ev_[w]) ev_free_.push_back(e);
             ev_[w].clear();
+            if (ms_out) ms_out[w] = ms;
+            if (n_out) n_out[w] = n;
         }
-        if (inter_ms) *inter_ms = ms[0];
-        if (inter_n) *inter_n = n[0];
-        if (intra_ms) *intra_ms = ms[1];
-        if (intra_n) *intra_n = n[1];
         return MOBI_OK;
     }
 
@@ -531,7 +536,6 @@ private:
         struct Off { size_t hdr, mbs, parts, ops, coefs, intra; };
         std::vector<Off> off(N_);
         L = StepLayout();
-        uint32_t max_intra = 0;
         for (int i = 0; i < N_; i++) if (views_[i].hdr) { L.job_stream.push_back(i); }
         L.n_jobs = (int)L.job_stream.size();
         size_t p = 0;
@@ -539,7 +543,6 @@ private:
         for (int j = 0; j < L.n_jobs; j++) {
             const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr;
             L.n_work += h.n_intra;
-            if (h.n_intra > max_intra) max_intra = h.n_intra;
             if (h.n_intra < h.n_mb) L.n_inter_jobs++;
             L.mbs += h.n_mb; L.intra_mbs += h.n_intra; L.inter_mbs += h.n_mb - h.n_intra;
             L.parts += h.n_parts; L.coefs += h.n_coefs; L.ops += h.n_ops; L.inter_coefs += h.n_inter_coefs;
@@ -584,13 +587,68 @@ private:
             J.flags = flags_ + (size_t)s * n_mb_;
             J.n_mb = h.n_mb; J.n_intra = h.n_intra;
         });
-        // intra work list: rank-major so that tickets of one picture ascend in decode order while
-        // different streams interleave (the wavefronts of all streams advance together)
+        // Intra work lists, each in dependency-depth order (depth = 1 + the deepest intra neighbour the macroblock
+        // waits for): tickets drawn in this order never wait for a ticket that has not been drawn yet, and
+        // macroblocks of equal depth -- of all pictures -- are independent, so the wavefronts of all streams advance
+        // together.  Intra macroblocks of P-pictures (shallow, many) and of I-pictures (deep chains, few) go to separate
+        // lists: they are launched on different CUDA streams so that the I-picture chains overlap the inter kernel.
         IntraWork* work = reinterpret_cast<IntraWork*>(a.h + L.work_off);
-        uint32_t w = 0;
-        for (uint32_t r = 0; r < max_intra; r++)
-            for (int j = 0; j < L.n_jobs; j++)
-                if (r < views_[L.job_stream[j]].hdr->n_intra) work[w++] = IntraWork{(uint32_t)j, r};
+        depth_.resize(L.n_jobs);
+        pool_.run(L.n_jobs, [&](int j) {
+            const mobi_packed_frame& f = views_[L.job_stream[j]];
+            const mobi_frame_hdr& h = *f.hdr;
+            std::vector<uint16_t>& dep = depth_[j];
+            dep.assign((size_t)h.n_mb + (size_t)h.n_intra * 2, 0);  // [0,n_mb): depth by MB; then (depth, wait) per rank
+            uint16_t* per_rank = dep.data() + h.n_mb;
+            for (uint32_t r = 0; r < h.n_intra; r++) {
+                const int m = (int)f.intra_list[r];
+                const uint32_t bits = (f.mbs[m].info >> 24) & 15u;
+                uint32_t wait = 0, d = 0;
+                for (int b = 0; b < 4; b++) {
+                    if (!((bits >> b) & 1u)) continue;
+                    const int nb = b == 0 ? m - 1 : m - g_.mbw - 2 + b;
+                    if (nb < 0 || nb >= m || (f.mbs[nb].info & 3u) != 1u) continue;
+                    wait |= 1u << b;
+                    if (dep[nb] > d) d = dep[nb];
+                }
+                dep[m] = (uint16_t)(d + 1);
+                per_rank[2 * r] = (uint16_t)(d + 1);
+                per_rank[2 * r + 1] = (uint16_t)wait;
+            }
+        });
+        {
+            uint32_t maxd = 0;
+            for (int j = 0; j < L.n_jobs; j++) {
+                const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr;
+                const uint16_t* per_rank = depth_[j].data() + h.n_mb;
+                for (uint32_t r = 0; r < h.n_intra; r++) if (per_rank[2 * r] > maxd) maxd = per_rank[2 * r];
+            }
+            bucket_.assign(2 * ((size_t)maxd + 2), 0);  // [list][depth]
+            uint32_t* cnt[2] = {bucket_.data(), bucket_.data() + maxd + 2};
+            for (int j = 0; j < L.n_jobs; j++) {
+                const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr;
+                const int list = h.n_intra == h.n_mb ? 1 : 0;
+                if (list) L.n_key_jobs++; else L.n_work_p += h.n_intra;
+                const uint16_t* per_rank = depth_[j].data() + h.n_mb;
+                for (uint32_t r = 0; r < h.n_intra; r++) cnt[list][per_rank[2 * r]]++;
+            }
+            uint32_t at = 0;
+            for (int list = 0; list < 2; list++)
+                for (uint32_t dd = 0; dd <= maxd + 1; dd++) { const uint32_t c = cnt[list][dd]; cnt[list][dd] = at; at += c; }
+            for (int j = 0; j < L.n_jobs; j++) {
+                const mobi_packed_frame& f = views_[L.job_stream[j]];
+                const mobi_frame_hdr& h = *f.hdr;
+                const int list = h.n_intra == h.n_mb ? 1 : 0;
+                const uint16_t* per_rank = depth_[j].data() + h.n_mb;
+                for (uint32_t r = 0; r < h.n_intra; r++) {
+                    const uint32_t m = f.intra_list[r];
+                    const mobi_mb& mb = f.mbs[m];
+                    IntraWork& w = work[cnt[list][per_rank[2 * r]]++];
+                    w.job = (uint32_t)j; w.mb = m; w.info = mb.info; w.first_op = mb.first_sub; w.first_coef = mb.first_coef;
+                    w.wait = per_rank[2 * r + 1]; w.pad[0] = w.pad[1] = 0;
+                }
+            }
+        }
         return MOBI_OK;
     }
     void rebase(uint8_t* h, const StepLayout& L, const uint8_t* from, uint8_t* to) {
@@ -608,21 +666,38 @@ private:
     }
     int launch_step(const uint8_t* d, const StepLayout& L) {
         const DevJob* jobs = reinterpret_cast<const DevJob*>(d + L.jobs_off);
-        if (L.n_inter_jobs) {
-            if (timing_) tick(0);
-            if (!ok(launch_inter(jobs, L.n_jobs, g_, stream_), "k_inter")) return MOBI_ERR_CUDA;
-            if (timing_) tick(0);
-            stats_.launches++;
-        }
-        if (L.n_work) {
+        const IntraWork* work = reinterpret_cast<const IntraWork*>(d + L.work_off);
+        const uint32_t n_key = L.n_work - L.n_work_p;
+        stamp_++;
+        if (n_key) {
+            // I-pictures: long dependency chains, little parallelism (about mbw/2 macroblocks per picture at a time).
+            // A few warps per picture on the side stream, concurrent with this step's inter kernel.
+            if (!ok(cudaEventRecord(fork_, stream_), "cudaEventRecord")) return MOBI_ERR_CUDA;
+            if (!ok(cudaStreamWaitEvent(side_, fork_, 0), "cudaStreamWaitEvent")) return MOBI_ERR_CUDA;
             uint32_t warps = 0;
-            stamp_++;
-            if (timing_) tick(1);
-            if (!ok(launch_intra(jobs, reinterpret_cast<const IntraWork*>(d + L.work_off), L.n_work, ticket_, ticket_base_, stamp_, g_, sm_count_, stream_, &warps), "k_intra")) return MOBI_ERR_CUDA;
-            if (timing_) tick(1);
-            ticket_base_ += L.n_work + warps;  // every warp draws exactly one ticket past the end
+            const uint32_t want = (uint32_t)L.n_key_jobs * (uint32_t)(g_.mbw < 8 ? 8 : g_.mbw);
+            if (timing_) tick(2, side_);
+            if (!ok(launch_intra(jobs, work + L.n_work_p, n_key, ticket_ + 32, ticket_base_[1], stamp_, g_, want, side_, &warps), "k_intra(I)")) return MOBI_ERR_CUDA;
+            if (timing_) tick(2, side_);
+            ticket_base_[1] += n_key + warps;  // every warp draws exactly one ticket past the end
+            stats_.launches++;
+            if (!ok(cudaEventRecord(join_, side_), "cudaEventRecord")) return MOBI_ERR_CUDA;
+        }
+        if (L.n_inter_jobs) {
+            if (timing_) tick(0, stream_);
+            if (!ok(launch_inter(jobs, L.n_jobs, g_, stream_), "k_inter")) return MOBI_ERR_CUDA;
+            if (timing_) tick(0, stream_);
             stats_.launches++;
         }
+        if (L.n_work_p) {
+            uint32_t warps = 0;
+            if (timing_) tick(1, stream_);
+            if (!ok(launch_intra(jobs, work, L.n_work_p, ticket_, ticket_base_[0], stamp_, g_, (uint32_t)sm_count_ * 32u, stream_, &warps), "k_intra(P)")) return MOBI_ERR_CUDA;
+            if (timing_) tick(1, stream_);
+            ticket_base_[0] += L.n_work_p + warps;
+            stats_.launches++;
+        }
+        if (n_key && !ok(cudaStreamWaitEvent(stream_, join_, 0), "cudaStreamWaitEvent")) return MOBI_ERR_CUDA;
         stats_.frames += L.n_jobs; stats_.mbs += L.mbs; stats_.inter_mbs += L.inter_mbs; stats_.intra_mbs += L.intra_mbs;
         stats_.parts += L.parts; stats_.coefs += L.coefs; stats_.ops += L.ops; stats_.inter_coefs += L.inter_coefs;
         return MOBI_OK;
@@ -642,6 +717,7 @@ private:
             if (kind > 1 || nsub > 64 || nco > 384) return set_err(MOBI_ERR_ARG, "packed frame: MB %u descriptor", m);
             if ((uint64_t)mb.first_coef + nco > h.n_coefs) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient range", m);
             if (kind == 1) {
+                if (nsub > 32) return set_err(MOBI_ERR_ARG, "packed frame: MB %u has more intra ops than any macroblock can (27)", m);
                 if ((uint64_t)mb.first_sub + nsub > h.n_ops) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op range", m);
                 if (mb.intra_rank >= h.n_intra || f.intra_list[mb.intra_rank] != m) return set_err(MOBI_ERR_ARG, "packed frame: MB %u intra rank", m);
                 n_intra++;
@@ -697,7 +773,11 @@ private:
     uint8_t* ring_ = nullptr;
     uint32_t* flags_ = nullptr;
     uint32_t* ticket_ = nullptr;
-    uint32_t ticket_base_ = 0, stamp_ = 0;
+    uint32_t ticket_base_[2] = {0, 0}, stamp_ = 0;
+    cudaStream_t side_ = nullptr;
+    cudaEvent_t fork_ = nullptr, join_ = nullptr;
+    std::vector<std::vector<uint16_t>> depth_;
+    std::vector<uint32_t> bucket_;
     Arena arena_[2];
     int cur_arena_ = 0;
     std::vector<Staged> staged_;
@@ -707,7 +787,7 @@ private:
     const uint8_t** ptr_d_ = nullptr;
     const uint8_t** ptr_h_ = nullptr;
     bool timing_ = false;
-    std::vector<cudaEvent_t> ev_[2], ev_free_;
+    std::vector<cudaEvent_t> ev_[3], ev_free_;
     OutSlot slot_[2];
     int slot_head_ = 0, slots_used_ = 0;
     mobi_batch_stats stats_{};
@@ -817,8 +897,8 @@ int mobi_batch_set_kernel_timing(mobi_batch_t* b, int enabled) {
     b->b.set_timing(enabled != 0);
     return MOBI_OK;
 }
-int mobi_batch_get_kernel_times(mobi_batch_t* b, double* inter_ms, uint64_t* inter_launches, double* intra_ms, uint64_t* intra_launches) {
-    return b ? b->b.kernel_times(inter_ms, inter_launches, intra_ms, intra_launches) : MOBI_ERR_ARG;
+int mobi_batch_get_kernel_times(mobi_batch_t* b, double ms[3], uint64_t launches[3]) {
+    return b ? b->b.kernel_times(ms, launches) : MOBI_ERR_ARG;
 }
 
 }  // extern "C"

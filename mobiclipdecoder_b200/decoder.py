@@ -317,10 +317,11 @@ class MobiBatch:
         self._check(self._lib.mobi_batch_set_kernel_timing(self._h, 1 if on else 0))
 
     def kernel_times(self):
-        """{'inter_ms', 'inter_launches', 'intra_ms', 'intra_launches'} since the last call (synchronises)."""
-        a, b, c, d = C.c_double(), C.c_uint64(), C.c_double(), C.c_uint64()
-        self._check(self._lib.mobi_batch_get_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
-        return {'inter_ms': a.value, 'inter_launches': b.value, 'intra_ms': c.value, 'intra_launches': d.value}
+        """Per-kernel device time since the last call (synchronises):
+        {'inter_ms', 'inter_launches', 'intra_ms', 'intra_launches', 'key_ms', 'key_launches'}."""
+        ms, n = (C.c_double * 3)(), (C.c_uint64 * 3)()
+        self._check(self._lib.mobi_batch_get_kernel_times(self._h, ms, n))
+        return {'inter_ms': ms[0], 'inter_launches': n[0], 'intra_ms': ms[1], 'intra_launches': n[1], 'key_ms': ms[2], 'key_launches': n[2]}
 
     def close(self):
         if getattr(self, '_h', None):
