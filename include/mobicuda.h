@@ -60,10 +60,13 @@ typedef struct mobi_mb {
     uint32_t info;         /* bits 0-1 kind: 0 inter, 1 intra; bits 2-8 n_sub (partitions <= 64, or intra ops <= 27);
                               bits 9-17 n_coefs (<= 384); bits 18-23 mask of 8x8 blocks holding >= 1 coefficient;
                               bits 24-27 (intra) neighbouring macroblocks whose pixels the predictors read:
-                              1 left (m-1), 2 top-left (m-mbw-1), 4 top (m-mbw), 8 top-right (m-mbw+1) */
+                              1 left (m-1), 2 top-left (m-mbw-1), 4 top (m-mbw), 8 top-right (m-mbw+1);
+                              bit 28 (inter) the single partition is also stored inline in intra_rank */
     uint32_t first_sub;    /* index of the first mobi_part (inter) or mobi_op (intra) */
     uint32_t first_coef;   /* index of the first mobi_coef */
-    uint32_t intra_rank;   /* intra MBs: position in the frame's intra list; inter: 0 */
+    uint32_t intra_rank;   /* intra MBs: position in the frame's intra list.  Inter MBs with info bit 28 set (exactly one
+                              partition, vector within 14 bits): that partition inline, mvx & 0x3FFF | (mvy & 0x3FFF) << 14
+                              | ref << 28 (the mobi_part record is emitted as well); otherwise 0 */
 } mobi_mb;                   /* 16 bytes */
 
 /* Motion partition leaf (MD:400-416 and clones): luma rect (x,y,w,h) inside the MB, ring index, half-pel vector. */

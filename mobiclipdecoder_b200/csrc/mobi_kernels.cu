@@ -100,128 +100,312 @@ __device__ __forceinline__ uint32_t mc_px(const uint8_t* p, int S, int phase) {
     return (((a >> 1) + (__ldg(p + 1) >> 1)) >> 1) + (((__ldg(p + S) >> 1) + (__ldg(p + S + 1) >> 1)) >> 1);
 }
 struct PartV { int mvx, mvy, ref; };
-__device__ __forceinline__ PartV ld_part(const mobi_part* p) {
-    uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
+__device__ __forceinline__ PartV part_of(uint32_t x, uint32_t y) {  // the two words of a mobi_part
     PartV v;
-    v.mvx = (int)(int16_t)(w.x >> 16);
-    v.mvy = (int)(int16_t)(w.y & 0xFFFFu);
-    v.ref = (int)((w.x >> 12) & 15u);
+    v.mvx = (int)(int16_t)(x >> 16);
+    v.mvy = (int)(int16_t)(y & 0xFFFFu);
+    v.ref = (int)((x >> 12) & 15u);
     return v;
+}
+// Four pixels + four residuals (transform outputs before >>6) -> saturated bytes.  cvt.pack.sat.u8.s32 packs two
+// clamped values per instruction: d = sat(a) << 8 | sat(b) | c << 16.  Saturation == Vx2MinMaxTable (MobiConst.cs:587)
+// on its whole domain.
+__device__ __forceinline__ uint32_t addsat4(uint32_t px, int r0, int r1, int r2, int r3) {
+    const int p0 = (int)(px & 255u) + (r0 >> 6), p1 = (int)((px >> 8) & 255u) + (r1 >> 6);
+    const int p2 = (int)((px >> 16) & 255u) + (r2 >> 6), p3 = (int)(px >> 24) + (r3 >> 6);
+    uint32_t hi, out;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(p3), "r"(p2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(p1), "r"(p0), "r"(hi));
+    return out;
 }
 
 // ------------------------------------------------------------------------------------------------
 // inter macroblocks
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DevJob* __restrict__ jobs, Geom g) {
-    __shared__ uint32_t s_qtab[80];
-    __shared__ __align__(16) int32_t s_coef[INTER_WARPS][6 * 64];
-    __shared__ __align__(4) uint8_t s_map[INTER_WARPS][64];
+// Reference pixels arrive by TMA: the whole ring is one rank-3 u8 tensor (Stride, 1.5*H, pictures), so a macroblock's
+// 16x16+halo luma window lies inside one 32x17 box and each chroma window inside one 32x9 box, fetched by one lane
+// straight into shared memory (TMA wants the innermost start coordinate 16-byte aligned -- an unaligned start raises
+// "illegal instruction" -- so boxes start at the window's column rounded down to 16 and lanes apply the remainder
+// when they read shared memory).  This takes the gathers off the LSU path, which is what bounds a load-per-lane formulation (every
+// warp-wide load touches 16 cache lines).  TMA zero-fills outside the tensor whereas the reference addresses its planes
+// flat (a column < 0 or >= Stride wraps into the neighbouring row), so windows that leave the row horizontally, and
+// macroblocks split into more than TMA_MAXP leaves, take the load-per-lane path instead.
+constexpr int TMA_MAXP = 2;
+constexpr uint32_t TMA_BYTES_L = 32 * 17, TMA_BYTES_C = 32 * 9;
 
+// Per-warp shared memory.  The reference windows are dead once the prediction is in registers, so the coefficient
+// blocks of the CODED 8x8 blocks (compacted: slot = rank of the block among the coded ones) reuse their space.
+struct InterSmem {
+    union {
+        struct {
+            uint8_t ref_l[TMA_MAXP][640];      // 32x17 luma boxes (128-byte aligned for TMA)
+            uint8_t ref_c[TMA_MAXP][2][384];   // 32x9 U and V boxes
+        } in;
+        int32_t coef[6][64];
+    } u;
+    uint8_t tile[384];     // prediction + residual: luma 16 rows x 16, then U 8x8, V 8x8
+    uint8_t map[64];       // 2x2-granular partition map of a split macroblock
+    uint2 parts[64];       // its leaf records
+    uint64_t bar;
+    uint8_t pad[56];
+};
+static_assert(sizeof(InterSmem) % 128 == 0, "per-warp shared memory must keep TMA destinations 128-byte aligned");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+// Same arithmetic as mc_row8 / mc_row4 on a box row held in shared memory (row pitch 32); p may have any alignment.
+__device__ __forceinline__ void lds_row8(const uint8_t* p, uint32_t& a0, uint32_t& a1, uint32_t& b0, uint32_t& b1) {
+    const uint32_t ad = smem_u32(p), sh = (ad & 3u) * 8u;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - (ad & 3u));
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+    a0 = __funnelshift_r(w0, w1, sh); a1 = __funnelshift_r(w1, w2, sh);
+    b0 = __funnelshift_rc(w0, w1, sh + 8u); b1 = __funnelshift_rc(w1, w2, sh + 8u);
+}
+__device__ __forceinline__ void tile_row8(const uint8_t* p, int phase, uint32_t& o0, uint32_t& o1) {
+    uint32_t a0, a1, b0, b1;
+    lds_row8(p, a0, a1, b0, b1);
+    if (phase == 0) { o0 = a0; o1 = a1; return; }
+    if (phase == 1) { o0 = half4(a0) + half4(b0); o1 = half4(a1) + half4(b1); return; }
+    uint32_t c0, c1, d0, d1;
+    lds_row8(p + 32, c0, c1, d0, d1);
+    if (phase == 2) { o0 = half4(a0) + half4(c0); o1 = half4(a1) + half4(c1); return; }
+    o0 = half4(half4(a0) + half4(b0)) + half4(half4(c0) + half4(d0));
+    o1 = half4(half4(a1) + half4(b1)) + half4(half4(c1) + half4(d1));
+}
+__device__ __forceinline__ void lds_row4(const uint8_t* p, uint32_t& a0, uint32_t& b0) {
+    const uint32_t ad = smem_u32(p), sh = (ad & 3u) * 8u;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - (ad & 3u));
+    const uint32_t w0 = q[0], w1 = q[1];
+    a0 = __funnelshift_r(w0, w1, sh);
+    b0 = __funnelshift_rc(w0, w1, sh + 8u);
+}
+__device__ __forceinline__ uint32_t tile_row4(const uint8_t* p, int phase) {
+    uint32_t a0, b0;
+    lds_row4(p, a0, b0);
+    if (phase == 0) return a0;
+    if (phase == 1) return half4(a0) + half4(b0);
+    uint32_t c0, d0;
+    lds_row4(p + 32, c0, d0);
+    if (phase == 2) return half4(a0) + half4(c0);
+    return half4(half4(a0) + half4(b0)) + half4(half4(c0) + half4(d0));
+}
+__device__ __forceinline__ uint32_t tile_px(const uint8_t* t, int pitch, int phase) {
+    const uint32_t a = t[0];
+    if (phase == 0) return a;
+    if (phase == 1) return (a >> 1) + (t[1] >> 1);
+    if (phase == 2) return (a >> 1) + (t[pitch] >> 1);
+    return (((a >> 1) + (t[1] >> 1)) >> 1) + (((t[pitch] >> 1) + (t[pitch + 1] >> 1)) >> 1);
+}
+
+template <int LOG2S>
+__global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DevJob* __restrict__ jobs, int mbw, int H,
+                                                           const __grid_constant__ CUtensorMap tm_l, const __grid_constant__ CUtensorMap tm_c) {
+    __shared__ __align__(128) InterSmem s_all[INTER_WARPS];
+    constexpr int S = 1 << LOG2S;
     const DevJob& J = jobs[blockIdx.y];
-    if (J.n_intra == J.n_mb) return;  // I-frame: nothing for this kernel
+    if (J.n_intra == J.n_mb) return;  // I-picture: nothing for this kernel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 80) s_qtab[threadIdx.x] = __ldg(&J.hdr->qtab[threadIdx.x]);
-    __syncthreads();
     const uint32_t mb = blockIdx.x * INTER_WARPS + warp;
     if (mb >= J.n_mb) return;
     const uint4 d = __ldg(reinterpret_cast<const uint4*>(J.mbs + mb));
     if (d.x & 3u) return;  // intra MB: k_intra's job
+    InterSmem& sm = s_all[warp];
+    const uint32_t bar = smem_u32(&sm.bar);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int n_parts = (int)((d.x >> 2) & 127u), n_coef = (int)((d.x >> 9) & 511u);
     const uint32_t blkmask = (d.x >> 18) & 63u;
-    const int S = g.S;
-    const int mbx = (int)(mb % (uint32_t)g.mbw), mby = (int)(mb / (uint32_t)g.mbw);
-    const size_t ysz = (size_t)S * g.H;
-    const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
+    const int mbx = (int)(mb % (uint32_t)mbw), mby = (int)(mb / (uint32_t)mbw);
+    const size_t ysz = (size_t)S * H;
+    const int yoff = ((mby * 16) << LOG2S) + mbx * 16, coff = yoff >> 1;
     const int lrow = lane >> 1, lhalf = lane & 1;
-    const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1;
-    const int ypix = yoff + lrow * S + lhalf * 8;                              // this lane's luma pixels
-    const int cpix = coff + (cpl ? (S >> 1) : 0) + crow * S + chalf * 4;       // this lane's chroma pixels
-    const mobi_part* parts = J.parts + d.y;
+    const int cpl = lane >> 4, crow = (lane >> 1) & 7;
+    const int ypix = yoff + (lrow << LOG2S) + lhalf * 8;                           // this lane's luma pixels
+    const int cpix = coff + (cpl ? (S >> 1) : 0) + (crow << LOG2S) + lhalf * 4;    // this lane's chroma pixels
+    // coefficient records do not depend on the prediction: fetch the first 32 now
+    const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs) + d.z;
+    uint32_t c_first = 0;
+    if (lane < n_coef) c_first = __ldg(cf + lane);
     uint32_t y0, y1, c0;
 
-    if (n_parts == 1) {
-        const PartV p = ld_part(parts);
-        const uint8_t* ref = J.ref[p.ref - 1];
-        mc_row8(ref + ypix + (p.mvy >> 1) * S + (p.mvx >> 1), S, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
-        const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-        c0 = mc_row4(ref + ysz + cpix + (cy >> 1) * S + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1));
+    // ---- leaf records: inline (unsplit macroblock), or loaded ----
+    PartV p0, p1;
+    p1.mvx = p1.mvy = 0; p1.ref = 1;
+    if (n_parts == 1 && (d.x & (1u << 28))) {  // the partition travels inside the descriptor: no dependent load
+        p0.mvx = ((int)(d.w << 18)) >> 18; p0.mvy = ((int)(d.w << 4)) >> 18; p0.ref = (int)(d.w >> 28);
     } else {
-        // partition map at 2x2-pixel granularity (leaves go down to 2x2, MD:1726)
-        uint8_t* map = s_map[warp];
-        for (int i = lane; i < n_parts; i += 32) {
-            const uint2 w = __ldg(reinterpret_cast<const uint2*>(parts + i));
-            const int x2 = w.x & 15, y2 = (w.x >> 4) & 15, cw = 1 << ((w.x >> 8) & 3), ch = 1 << ((w.x >> 10) & 3);
-            for (int yy = 0; yy < ch; yy++) for (int xx = 0; xx < cw; xx++) map[(y2 + yy) * 8 + x2 + xx] = (uint8_t)i;
-        }
+        const mobi_part* parts = J.parts + d.y;
+        for (int i = lane; i < n_parts; i += 32) sm.parts[i] = __ldg(reinterpret_cast<const uint2*>(parts + i));
         __syncwarp();
-        const uint32_t ml = *reinterpret_cast<const uint32_t*>(map + (lrow >> 1) * 8 + lhalf * 4);
-        if (ml == (ml & 255u) * 0x01010101u) {
-            const PartV p = ld_part(parts + (ml & 255u));
-            mc_row8(J.ref[p.ref - 1] + ypix + (p.mvy >> 1) * S + (p.mvx >> 1), S, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
+        { const uint2 w = sm.parts[0]; p0 = part_of(w.x, w.y); }
+        if (n_parts > 1) { const uint2 w = sm.parts[1]; p1 = part_of(w.x, w.y); }
+    }
+    // Can the windows be fetched as TMA boxes?  Only when every column they need lies inside its own pixel row.
+    bool tma = n_parts <= TMA_MAXP;
+    {
+        const int x0 = mbx * 16 + (p0.mvx >> 1), cx0 = mbx * 8 + (p0.mvx >> 2);
+        tma = tma && x0 >= 0 && x0 + 17 <= S && cx0 >= 0 && cx0 + 9 <= (S >> 1);
+        if (n_parts == 2) {
+            const int x1 = mbx * 16 + (p1.mvx >> 1), cx1 = mbx * 8 + (p1.mvx >> 2);
+            tma = tma && x1 >= 0 && x1 + 17 <= S && cx1 >= 0 && cx1 + 9 <= (S >> 1);
+        }
+    }
+    if (tma) {
+        __syncwarp();  // barrier initialised
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)n_parts * (TMA_BYTES_L + 2 * TMA_BYTES_C);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+            for (int i = 0; i < n_parts; i++) {
+                const PartV p = i ? p1 : p0;
+                const int pic = (int)J.ref_pic[p.ref - 1];
+                const int cx = p.mvx >> 1, cy = p.mvy >> 1;
+                const int xl = mbx * 16 + (p.mvx >> 1), xc = mbx * 8 + (cx >> 1);
+                tma_load_3d(smem_u32(sm.u.in.ref_l[i]), &tm_l, xl & ~15, mby * 16 + (p.mvy >> 1), pic, bar);
+                tma_load_3d(smem_u32(sm.u.in.ref_c[i][0]), &tm_c, xc & ~15, H + mby * 8 + (cy >> 1), pic, bar);
+                tma_load_3d(smem_u32(sm.u.in.ref_c[i][1]), &tm_c, (S >> 1) + (xc & ~15), H + mby * 8 + (cy >> 1), pic, bar);
+            }
+        }
+    }
+
+    // ---- which leaf covers each of this lane's 2x2 cells (split macroblocks) ----
+    uint32_t ml = 0, mc = 0;
+    if (n_parts > 1) {
+        // Partition map at 2x2-pixel granularity (leaves go down to 2x2, MD:1726), built cell-parallel: lane l owns
+        // cells 2l and 2l+1 of the 8x8 cell grid and tests them against every leaf rectangle.
+        const int cy2 = lane >> 2, cx2 = (lane & 3) * 2;
+        uint32_t i0 = 0, i1 = 0;
+        for (int i = 0; i < n_parts; i++) {
+            const uint32_t w = sm.parts[i].x;
+            const int x2 = w & 15, y2 = (w >> 4) & 15, cw = 1 << ((w >> 8) & 3), ch = 1 << ((w >> 10) & 3);
+            const bool rowin = (unsigned)(cy2 - y2) < (unsigned)ch;
+            if (rowin && (unsigned)(cx2 - x2) < (unsigned)cw) i0 = (uint32_t)i;
+            if (rowin && (unsigned)(cx2 + 1 - x2) < (unsigned)cw) i1 = (uint32_t)i;
+        }
+        reinterpret_cast<uint16_t*>(sm.map)[lane] = (uint16_t)(i0 | i1 << 8);
+        __syncwarp();
+        ml = *reinterpret_cast<const uint32_t*>(sm.map + (lrow >> 1) * 8 + lhalf * 4);
+        mc = *reinterpret_cast<const uint32_t*>(sm.map + crow * 8 + lhalf * 4);
+    }
+    const bool l_uni = ml == (ml & 255u) * 0x01010101u, c_uni = mc == (mc & 255u) * 0x01010101u;
+
+    if (tma) {
+        uint32_t done;
+        do {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+        } while (!done);
+        if (l_uni) {
+            const int i = (int)(ml & 255u);
+            const PartV p = i ? p1 : p0;
+            tile_row8(sm.u.in.ref_l[i] + lrow * 32 + ((mbx * 16 + (p.mvx >> 1)) & 15) + lhalf * 8, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
         } else {
             uint32_t o[2] = {0, 0};
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const PartV p = ld_part(parts + ((ml >> (8 * c)) & 255u));
-                const uint8_t* s = J.ref[p.ref - 1] + ypix + 2 * c + (p.mvy >> 1) * S + (p.mvx >> 1);
+                const int i = (int)((ml >> (8 * c)) & 255u);
+                const PartV p = i ? p1 : p0;
+                const uint8_t* t = sm.u.in.ref_l[i] + lrow * 32 + ((mbx * 16 + (p.mvx >> 1)) & 15) + lhalf * 8 + 2 * c;
+                const int ph = (p.mvx & 1) | ((p.mvy & 1) << 1);
+                o[c >> 1] |= (tile_px(t, 32, ph) | tile_px(t + 1, 32, ph) << 8) << (16 * (c & 1));
+            }
+            y0 = o[0]; y1 = o[1];
+        }
+        if (c_uni) {
+            const int i = (int)(mc & 255u);
+            const PartV p = i ? p1 : p0;
+            const int cx = p.mvx >> 1, cy = p.mvy >> 1;
+            c0 = tile_row4(sm.u.in.ref_c[i][cpl] + crow * 32 + ((mbx * 8 + (cx >> 1)) & 15) + lhalf * 4, (cx & 1) | ((cy & 1) << 1));
+        } else {
+            c0 = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int i = (int)((mc >> (8 * c)) & 255u);
+                const PartV p = i ? p1 : p0;
+                const int cx = p.mvx >> 1, cy = p.mvy >> 1;
+                c0 |= tile_px(sm.u.in.ref_c[i][cpl] + crow * 32 + ((mbx * 8 + (cx >> 1)) & 15) + lhalf * 4 + c, 32, (cx & 1) | ((cy & 1) << 1)) << (8 * c);
+            }
+        }
+        __syncwarp();  // all lanes are done with the windows before the coefficient blocks overwrite them
+    } else {
+        auto leaf = [&](uint32_t idx) { if (n_parts == 1) return p0; const uint2 w = sm.parts[idx]; return part_of(w.x, w.y); };
+        if (l_uni) {
+            const PartV p = leaf(ml & 255u);
+            mc_row8(J.ref[p.ref - 1] + ypix + ((p.mvy >> 1) << LOG2S) + (p.mvx >> 1), S, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
+        } else {
+            uint32_t o[2] = {0, 0};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const PartV p = leaf((ml >> (8 * c)) & 255u);
+                const uint8_t* s = J.ref[p.ref - 1] + ypix + 2 * c + ((p.mvy >> 1) << LOG2S) + (p.mvx >> 1);
                 const int ph = (p.mvx & 1) | ((p.mvy & 1) << 1);
                 const uint32_t v = mc_px(s, S, ph) | mc_px(s + 1, S, ph) << 8;
                 o[c >> 1] |= v << (16 * (c & 1));
             }
             y0 = o[0]; y1 = o[1];
         }
-        const uint32_t mc = *reinterpret_cast<const uint32_t*>(map + crow * 8 + chalf * 4);
-        if (mc == (mc & 255u) * 0x01010101u) {
-            const PartV p = ld_part(parts + (mc & 255u));
+        if (c_uni) {
+            const PartV p = leaf(mc & 255u);
             const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-            c0 = mc_row4(J.ref[p.ref - 1] + ysz + cpix + (cy >> 1) * S + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1));
+            c0 = mc_row4(J.ref[p.ref - 1] + ysz + cpix + ((cy >> 1) << LOG2S) + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1));
         } else {
             c0 = 0;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const PartV p = ld_part(parts + ((mc >> (8 * c)) & 255u));
+                const PartV p = leaf((mc >> (8 * c)) & 255u);
                 const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                c0 |= mc_px(J.ref[p.ref - 1] + ysz + cpix + c + (cy >> 1) * S + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1)) << (8 * c);
+                c0 |= mc_px(J.ref[p.ref - 1] + ysz + cpix + c + ((cy >> 1) << LOG2S) + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1)) << (8 * c);
             }
         }
     }
 
     if (n_coef) {
-        int32_t* cb = s_coef[warp];
-        for (int i = lane; i < 96; i += 32) reinterpret_cast<int4*>(cb)[i] = make_int4(0, 0, 0, 0);
+        // ---- dequantise into the compacted coefficient blocks (MD:3424-3429) ----
+        const int nblk = __popc(blkmask);
+        for (int i = lane; i < nblk * 16; i += 32) reinterpret_cast<int4*>(&sm.u.coef[0][0])[i] = make_int4(0, 0, 0, 0);
+        *reinterpret_cast<uint2*>(sm.tile + lrow * 16 + lhalf * 8) = make_uint2(y0, y1);
+        *reinterpret_cast<uint32_t*>(sm.tile + 256 + cpl * 64 + crow * 8 + lhalf * 4) = c0;
         __syncwarp();
+        const uint32_t* __restrict__ qtab = J.hdr->qtab;
         uint32_t m8 = 0;
-        const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs + d.z);
         for (int j = lane; j < n_coef; j += 32) {
-            const uint32_t c = __ldg(cf + j);
+            const uint32_t c = j < 32 ? c_first : __ldg(cf + j);
             const int level = (int)(int16_t)(c & 0xFFFFu);
             const uint32_t pos = (c >> 16) & 63u, sub = (c >> 22) & 3u, blk = (c >> 24) & 7u, is8 = c >> 31;
-            const uint32_t w = s_qtab[is8 ? pos : 64u + pos];
-            const int val = (int)(w >> 8) * level;  // MD:3427-3429
-            cb[blk * 64u + (is8 ? (w & 63u) : sub * 16u + (w & 15u))] = val;
+            const uint32_t w = __ldg(qtab + (is8 ? pos : 64u + (pos & 15u)));
+            const uint32_t slot = __popc(blkmask & ((1u << blk) - 1u));
+            sm.u.coef[slot][is8 ? (w & 63u) : sub * 16u + (w & 15u)] = (int)(w >> 8) * level;
             m8 |= is8 << blk;
         }
         m8 = __reduce_or_sync(0xffffffffu, m8);
+        // ids of the coded blocks, one nibble each, in slot order
+        uint32_t list = 0;
+        {
+            int n = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) if ((blkmask >> k) & 1u) { list |= (uint32_t)k << (4 * n); n++; }
+        }
         __syncwarp();
 
-        int32_t in[8], v[8];
-        // ---- luma: lane (block lb, row r) ----
-        if (blkmask & 15u) {
-            const int lb = ((lane >> 4) << 1) | (lane & 1), r = (lane >> 1) & 7, i4 = r & 3, s0 = (r >> 2) * 2;
-            const bool has = (blkmask >> lb) & 1u, is8 = (m8 >> lb) & 1u;
-            int32_t* B = cb + lb * 64;
+        // ---- inverse transforms: eight lanes per coded block (one row each), four blocks per pass ----
+        const int g = lane >> 3, r = lane & 7, i4 = r & 3, s0 = (r >> 2) * 2;
+        for (int base = 0; base < nblk; base += 4) {
+            const int slot = base + g;
+            const bool has = slot < nblk;
+            const int b = (int)((list >> (4 * slot)) & 7u);
+            const bool is8 = (m8 >> b) & 1u;
+            int32_t* B = sm.u.coef[has ? slot : 0];
+            int32_t in[8], v[8];
             if (has) {
-                if (is8) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) in[k] = B[8 * r + k];
-                    if (r == 0) in[0] += 32;
-                    bfly8(in, v);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) { in[k] = B[s0 * 16 + 4 * i4 + k]; in[4 + k] = B[(s0 + 1) * 16 + 4 * i4 + k]; }
-                    if (i4 == 0) { in[0] += 32; in[4] += 32; }
-                    bfly4(in, v); bfly4(in + 4, v + 4);
-                }
+                const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r : s0 * 16 + 4 * i4));
+                const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r + 4 : (s0 + 1) * 16 + 4 * i4));
+                in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
+                if (is8) { if (r == 0) in[0] += 32; bfly8(in, v); }
+                else { if (i4 == 0) { in[0] += 32; in[4] += 32; } bfly4(in, v); bfly4(in + 4, v + 4); }
             }
             __syncwarp();
             if (has) {
@@ -235,63 +419,22 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DevJob* __rest
             }
             __syncwarp();
             if (has) {
-                if (is8) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) in[k] = B[8 * r + k];
-                    bfly8(in, v);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) { in[k] = B[s0 * 16 + 4 * i4 + k]; in[4 + k] = B[(s0 + 1) * 16 + 4 * i4 + k]; }
-                    bfly4(in, v); bfly4(in + 4, v + 4);
-                }
-                y0 = addclip4(y0, v); y1 = addclip4(y1, v + 4);
-            }
-        }
-        // ---- chroma: lane (plane cpl, row crow, half chalf); the 8-point passes are computed by both halves ----
-        if (blkmask & 48u) {
-            const int cbk = 4 + cpl, r = crow, i4 = r & 3, s = (r >> 2) * 2 + chalf;
-            const bool has = (blkmask >> cbk) & 1u, is8 = (m8 >> cbk) & 1u;
-            int32_t* B = cb + cbk * 64;
-            if (has) {
-                if (is8) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) in[k] = B[8 * r + k];
-                    if (r == 0) in[0] += 32;
-                    bfly8(in, v);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) in[k] = B[s * 16 + 4 * i4 + k];
-                    if (i4 == 0) in[0] += 32;
-                    bfly4(in, v);
-                }
+                const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r : s0 * 16 + 4 * i4));
+                const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r + 4 : (s0 + 1) * 16 + 4 * i4));
+                in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
+                if (is8) bfly8(in, v); else { bfly4(in, v); bfly4(in + 4, v + 4); }
+                // either way the lane now holds the residuals of row r, columns 0..7 of block b: add onto the prediction
+                uint8_t* t = b < 4 ? sm.tile + ((b >> 1) * 8 + r) * 16 + (b & 1) * 8 : sm.tile + 256 + (b - 4) * 64 + r * 8;
+                uint2 px = *reinterpret_cast<uint2*>(t);
+                px.x = addsat4(px.x, v[0], v[1], v[2], v[3]);
+                px.y = addsat4(px.y, v[4], v[5], v[6], v[7]);
+                *reinterpret_cast<uint2*>(t) = px;
             }
             __syncwarp();
-            if (has) {
-                if (is8) {
-                    if (chalf == 0) {
-#pragma unroll
-                        for (int k = 0; k < 8; k++) B[8 * k + r] = v[k];
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) B[s * 16 + 4 * k + i4] = v[k];
-                }
-            }
-            __syncwarp();
-            if (has) {
-                if (is8) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) in[k] = B[8 * r + k];
-                    bfly8(in, v);
-                    c0 = addclip4(c0, chalf ? v + 4 : v);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) in[k] = B[s * 16 + 4 * i4 + k];
-                    bfly4(in, v);
-                    c0 = addclip4(c0, v);
-                }
-            }
         }
+        const uint2 yy = *reinterpret_cast<const uint2*>(sm.tile + lrow * 16 + lhalf * 8);
+        y0 = yy.x; y1 = yy.y;
+        c0 = *reinterpret_cast<const uint32_t*>(sm.tile + 256 + cpl * 64 + crow * 8 + lhalf * 4);
     }
 
     *reinterpret_cast<uint2*>(J.dst + ypix) = make_uint2(y0, y1);
@@ -631,10 +774,12 @@ __global__ void __launch_bounds__(256) k_pack_i420(const uint8_t* const* __restr
 
 }  // namespace
 
-cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, cudaStream_t st) {
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, cudaStream_t st) {
     if (n_jobs <= 0) return cudaSuccess;
     dim3 grid((unsigned)((g.mbw * g.mbh + INTER_WARPS - 1) / INTER_WARPS), (unsigned)n_jobs);
-    k_inter<<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g);
+    if (g.log2S == 8) k_inter<8><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, g.H, tm_l, tm_c);
+    else if (g.log2S == 9) k_inter<9><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, g.H, tm_l, tm_c);
+    else k_inter<10><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, g.H, tm_l, tm_c);
     return cudaGetLastError();
 }
 

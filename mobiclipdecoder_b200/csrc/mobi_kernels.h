@@ -1,6 +1,7 @@
 // Device-side job table and kernel launchers (implemented in mobi_kernels.cu).
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "../../include/mobicuda.h"
 
@@ -18,7 +19,8 @@ struct alignas(16) DevJob {
     const uint8_t* ref[5];   // ref[k-1]: luma plane of ring picture k (Y[k], MD:413); null when absent
     uint32_t* flags;         // per-MB completion stamps of this stream (intra wavefront)
     uint32_t n_mb, n_intra;
-    uint32_t pad[2];
+    uint32_t dst_pic;        // index of dst / ref[k-1] along the picture axis of the ring tensor (TMA coordinates)
+    uint32_t ref_pic[5];
 };
 
 // One intra macroblock to reconstruct: its descriptor travels with the work item so that the warp needs no dependent
@@ -31,7 +33,8 @@ struct Geom {
 };
 
 // Inter macroblocks of every job: MC from the ring + dequant/IDCT/add/clip.  One warp per MB.
-cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, cudaStream_t st);
+// tm_l / tm_c: the ring as a rank-3 u8 tensor (Stride, 1.5*H, pictures) with boxes 32x17x1 (luma windows) and 32x9x1 (chroma windows).
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, cudaStream_t st);
 // Intra macroblocks (I-frames and intra MBs of P-frames) as a dependency wavefront.  One warp per MB; work is handed
 // out through an atomic ticket in dependency-depth order so that a waiting warp's dependencies are always running.
 // *warps_launched receives the number of warps started: each draws exactly one ticket past n_work, so the

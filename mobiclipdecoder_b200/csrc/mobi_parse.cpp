@@ -396,6 +396,13 @@ struct FrameParse {
         uint32_t np = (uint32_t)out.parts.size() - first_part, nco = (uint32_t)out.coefs.size() - first_coef;
         mb.info = 0u | np << 2 | nco << 9 | mask << 18;
         mb.first_sub = first_part; mb.first_coef = first_coef; mb.intra_rank = 0;
+        if (np == 1) {  // an unsplit macroblock carries its vector inside the descriptor (saves the device a dependent load)
+            const mobi_part& p = out.parts[first_part];
+            if (p.mvx >= -8192 && p.mvx < 8192 && p.mvy >= -8192 && p.mvy < 8192) {
+                mb.info |= 1u << 28;
+                mb.intra_rank = ((uint32_t)p.mvx & 0x3FFFu) | ((uint32_t)p.mvy & 0x3FFFu) << 14 | (uint32_t)(p.shape >> 4) << 28;
+            }
+        }
         out.mbs.push_back(mb);
         out.hdr.n_inter_coefs += nco;
     }

@@ -11,7 +11,9 @@
 //             uploaded with a single cudaMemcpyAsync.  Two arenas alternate so that the host parses step
 //             k+1 while the GPU reconstructs step k.
 //   staged    device-resident copies of whole steps for the kernel-only replay (bench "value" leg, ncu).
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
 #include <atomic>
 #include <condition_variable>
 #include <cstdarg>
@@ -191,6 +193,27 @@ public:
         if (!ok(cudaMalloc(&ptr_d_, sizeof(void*) * (size_t)N_), "cudaMalloc(ptrs)")) return MOBI_ERR_NOMEM;
         if (!ok(cudaMallocHost(&ptr_h_, sizeof(void*) * (size_t)N_), "cudaMallocHost(ptrs)")) return MOBI_ERR_NOMEM;
         if (!ok(cudaStreamSynchronize(stream_), "init sync")) return MOBI_ERR_CUDA;
+        return make_tensor_maps();
+    }
+    // The ring as one rank-3 u8 tensor (Stride, 1.5*H, pictures): a picture's chroma rows follow its luma rows at the
+    // same pitch, pictures are pic_ bytes apart.  cuTensorMapEncodeTiled is reached through the runtime so that the
+    // library does not link libcuda.
+    int make_tensor_maps() {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (!ok(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres), "cudaGetDriverEntryPoint") || !fn || qres != cudaDriverEntryPointSuccess)
+            return set_err(MOBI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+        const cuuint64_t dims[3] = {(cuuint64_t)g_.S, (cuuint64_t)H_ * 3 / 2, (cuuint64_t)N_ * RING};
+        const cuuint64_t strides[2] = {(cuuint64_t)g_.S, (cuuint64_t)pic_};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const cuuint32_t box_l[3] = {32, 17, 1}, box_c[3] = {32, 9, 1};
+        CUresult r = encode(&tm_l_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ring_, dims, strides, box_l, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+            r = encode(&tm_c_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ring_, dims, strides, box_c, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_err(MOBI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
         return MOBI_OK;
     }
 
@@ -584,6 +607,8 @@ private:
             const int c = count[s];
             J.dst = picture(s, c);
             for (int k = 1; k <= 5; k++) J.ref[k - 1] = k <= c ? picture(s, c - k) : nullptr;
+            J.dst_pic = (uint32_t)(s * RING + c % RING);
+            for (int k = 1; k <= 5; k++) J.ref_pic[k - 1] = k <= c ? (uint32_t)(s * RING + (c - k) % RING) : 0u;
             J.flags = flags_ + (size_t)s * n_mb_;
             J.n_mb = h.n_mb; J.n_intra = h.n_intra;
         });
@@ -685,7 +710,7 @@ private:
         }
         if (L.n_inter_jobs) {
             if (timing_) tick(0, stream_);
-            if (!ok(launch_inter(jobs, L.n_jobs, g_, stream_), "k_inter")) return MOBI_ERR_CUDA;
+            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_l_, tm_c_, stream_), "k_inter")) return MOBI_ERR_CUDA;
             if (timing_) tick(0, stream_);
             stats_.launches++;
         }
@@ -724,6 +749,12 @@ private:
                 continue;
             }
             if (nsub == 0 || (uint64_t)mb.first_sub + nsub > h.n_parts) return set_err(MOBI_ERR_ARG, "packed frame: MB %u partition range", m);
+            if ((mb.info >> 28) & 1u) {  // inline copy of the single partition must agree with the record that is range-checked below
+                const mobi_part& p = f.parts[mb.first_sub];
+                const uint32_t want = ((uint32_t)p.mvx & 0x3FFFu) | ((uint32_t)p.mvy & 0x3FFFu) << 14 | (uint32_t)(p.shape >> 4) << 28;
+                if (nsub != 1 || mb.intra_rank != want || p.mvx < -8192 || p.mvx >= 8192 || p.mvy < -8192 || p.mvy >= 8192)
+                    return set_err(MOBI_ERR_ARG, "packed frame: MB %u inline partition", m);
+            }
             const int mbx = (int)(m % (uint32_t)g_.mbw), mby = (int)(m / (uint32_t)g_.mbw);
             uint64_t cover[4] = {0, 0, 0, 0};  // 16x16 luma pixels
             for (uint32_t k = 0; k < nsub; k++) {
@@ -774,6 +805,7 @@ private:
     uint32_t* flags_ = nullptr;
     uint32_t* ticket_ = nullptr;
     uint32_t ticket_base_[2] = {0, 0}, stamp_ = 0;
+    CUtensorMap tm_l_, tm_c_;
     cudaStream_t side_ = nullptr;
     cudaEvent_t fork_ = nullptr, join_ = nullptr;
     std::vector<std::vector<uint16_t>> depth_;
