@@ -97,6 +97,9 @@ struct FrameParse {
         for (int i = 0; i < 16; i++) P.st_.qtab[64 + i] = (uint32_t)MOBI_SCAN4[i] | (uint32_t)MOBI_SCALE4[row * 16 + i] << sh;
         sh -= 2;
         for (int i = 0; i < 64; i++) P.st_.qtab[i] = (uint32_t)MOBI_SCAN8[i] | (uint32_t)MOBI_SCALE8[row * 64 + i] << sh;
+        bool clean = true;  // q < 12 on ModsDS lets the scale leak into the matrix-index byte (MD:3909-3911 vs MD:3426)
+        for (int i = 0; i < 80; i++) if ((P.st_.qtab[i] & 0xFF) >= (i < 64 ? 64u : 16u)) clean = false;
+        P.st_.qtab_clean = clean;
         uint8_t* c = P.st_.ctx;
         c[1] = c[2] = c[3] = c[4] = 9; c[8] = c[0x10] = c[0x18] = c[0x20] = 9;
     }
@@ -155,7 +158,7 @@ struct FrameParse {
             pos += (uint32_t)run;
             // The reference indexes Internal[] with no check: a run past the block walks into the next table.
             if (pos >= (uint32_t)n) fail(MOBI_ERR_BITSTREAM, "coefficient run past end of block");
-            if ((qt[pos] & 0xFF) >= 64u) fail(MOBI_ERR_BITSTREAM, "quantiser < 12 corrupts the scan table (MD:3909-3911)");
+            if (!P.st_.qtab_clean && (qt[pos] & 0xFF) >= 64u) fail(MOBI_ERR_BITSTREAM, "quantiser < 12 corrupts the scan table (MD:3909-3911)");
             mobi_coef c;
             c.level = (int16_t)level;
             c.pos = (uint8_t)(pos | (uint32_t)sub << 6);
@@ -443,6 +446,7 @@ struct FrameParse {
                     mvpx = med3(e[0], e[2], e[4]); mvpy = med3(e[1], e[3], e[5]);
                     int slot = 2 * (mx + 1);
                     P.mvc_[slot] = P.mvc_[slot + 1] = 0;
+                    out.room_for_mb();
                     inter_mb(off, slot);
                     off += 16; w -= 16; mx++;
                 } while (w > 0);
@@ -461,6 +465,7 @@ struct FrameParse {
                 do {
                     uint32_t sub = b.win >> 31;
                     b.win += b.win; b.nb--; b.chk();
+                    out.room_for_mb();
                     intra_mb(sub != 0, off);
                     off += 16; w -= 16;
                 } while (w > 0);

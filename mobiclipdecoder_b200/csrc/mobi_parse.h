@@ -9,14 +9,30 @@
 
 namespace mobi {
 
+// Append-only array whose capacity is topped up once per macroblock (room(k) guarantees k more unchecked appends),
+// so the per-coefficient / per-leaf hot loops carry no capacity checks.
+template <class T>
+struct Arr {
+    std::vector<T> v;
+    size_t n = 0;
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    void room(size_t k) { if (n + k > v.size()) v.resize((n + k) * 2); }
+    void push_back(const T& x) { v[n++] = x; }
+    T& operator[](size_t i) { return v[i]; }
+    const T* data() const { return v.data(); }
+};
+
 struct ParsedFrame {
     mobi_frame_hdr hdr;
-    std::vector<mobi_mb> mbs;
-    std::vector<mobi_part> parts;
-    std::vector<mobi_op> ops;
-    std::vector<mobi_coef> coefs;
-    std::vector<uint32_t> intra;
+    Arr<mobi_mb> mbs;
+    Arr<mobi_part> parts;
+    Arr<mobi_op> ops;
+    Arr<mobi_coef> coefs;
+    Arr<uint32_t> intra;
     void clear() { mbs.clear(); parts.clear(); ops.clear(); coefs.clear(); intra.clear(); }
+    // worst case of one macroblock: 64 leaves (2x2), 27 intra ops, 6 x 64 coefficients
+    void room_for_mb() { mbs.room(1); parts.room(64); ops.room(32); coefs.room(384); intra.room(1); }
     mobi_packed_frame view() const { return mobi_packed_frame{&hdr, mbs.data(), parts.data(), ops.data(), coefs.data(), intra.data()}; }
 };
 
@@ -44,6 +60,7 @@ private:
         uint32_t qtab[80] = {0};  // Internal[10..89]
         uint8_t ctx[40] = {0};    // Internal bytes 0..39: intra-mode context grid
         int decoded = 0;          // pictures currently in the ring (saturates at 6)
+        bool qtab_clean = true;   // every matrix index in qtab is in range (always, unless ModsDS runs with q < 12)
     };
     struct Bits;
     friend struct FrameParse;

@@ -185,6 +185,14 @@ class MobiParser:
             pass
 
 
+class _PackedInputs:
+    """One step's frames in one host buffer plus the argument tables of mobi_batch_decode (see MobiBatch.pack_inputs)."""
+    __slots__ = ('blob', 'ptrs', 'lens', 'offs')
+
+    def __init__(self, blob, ptrs, lens, offs):
+        self.blob, self.ptrs, self.lens, self.offs = blob, ptrs, lens, offs
+
+
 class MobiBatch:
     """N independent streams of one geometry advancing in lock step on one GPU (mobi_batch_*)."""
 
@@ -208,7 +216,27 @@ class MobiBatch:
         if rc != 0:
             raise MobiError(rc, self._lib.mobi_batch_last_error(self._h).decode())
 
+    def pack_inputs(self, frames, offsets=None):
+        """Marshal one step's arguments once: the frames are laid end to end in one host buffer and the pointer /
+        length / offset tables the C call takes are built from it.  Pass the result to decode / submit / stage in
+        place of the list to keep per-call Python overhead out of the way (a C# or C caller passes such tables as is)."""
+        if len(frames) != self.n_streams:
+            raise ValueError('need one frame per stream')
+        lens = np.fromiter((len(f) for f in frames), dtype=np.int32, count=self.n_streams)
+        starts = np.zeros(self.n_streams, dtype=np.int64)
+        np.cumsum(lens[:-1], out=starts[1:])
+        blob = np.frombuffer(b''.join(bytes(f) if not isinstance(f, (bytes, bytearray)) else f for f in frames), dtype=np.uint8)
+        ptrs = (starts + blob.ctypes.data).astype(np.uint64)
+        offs = np.zeros(self.n_streams, dtype=np.int32) if offsets is None else np.asarray(offsets, dtype=np.int32).copy()
+        return _PackedInputs(blob, ptrs, lens, offs)
+
     def _marshal(self, frames, offsets):
+        if isinstance(frames, _PackedInputs):
+            C.memmove(self._ptrs, frames.ptrs.ctypes.data, 8 * self.n_streams)
+            C.memmove(self._lens, frames.lens.ctypes.data, 4 * self.n_streams)
+            C.memmove(self._offs, frames.offs.ctypes.data, 4 * self.n_streams)
+            self._keep = frames
+            return
         if len(frames) != self.n_streams:
             raise ValueError('need one frame per stream')
         keep = []
@@ -235,7 +263,7 @@ class MobiBatch:
         """Pipelined decode (mobi_batch_submit): returns at once; at most two results may be outstanding."""
         self._marshal(frames, offsets)
         self._check(self._lib.mobi_batch_submit(self._h, self._ptrs, self._lens, self._offs, self._status, fmt))
-        return list(self._offs), list(self._status)
+        return self._offs, self._status
 
     def fetch(self, out=None, copy=True):
         """Oldest outstanding result as uint8 [n_streams, bytes per stream].  copy=False returns a view of the

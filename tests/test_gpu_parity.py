@@ -117,3 +117,76 @@ def test_error_behaviour_matches_reference_null():
         assert ora.decode(data, 0, False)[0]
     assert np.array_equal(dec.Y[0], ora.y) and np.array_equal(dec.UV[0], ora.uv)
     dec.close()
+
+
+def test_config2_full_size_1024_preparsed_p_pictures():
+    """BASELINE config 2 at full size: 1024 independent (reference picture, P-picture) pairs at 256x192 from seeds
+    1..1024, parsed and uploaded once (mobi_batch_stage), reconstructed by the kernels alone (mobi_batch_replay), every
+    plane of every stream compared with the oracle."""
+    name, n_streams = 'pframes_256x192', 1024
+    w, h, ver, _ = CONFIGS[name]
+    streams = [frames(name, 1 + s, 2) for s in range(n_streams)]
+    b = MobiBatch(w, h, ver, n_streams)
+    for f in range(2):
+        b.stage([streams[s][f][0] for s in range(n_streams)])
+    b.reset()
+    b.replay(0, 2)
+    got = b.read_yuv()
+    for s in range(n_streams):
+        o = Oracle(w, h, ver)
+        assert o.decode(streams[s][0][0], 0, False)[0] and o.decode(streams[s][1][0], 0, False)[0]
+        assert np.array_equal(got[s], o.i420()), 'stream %d (seed %d)' % (s, 1 + s)
+    st = b.stats()
+    assert st['frames'] == 2 * n_streams and st['inter_mbs'] == n_streams * (w // 16) * (h // 16)
+    b.close()
+
+
+@pytest.mark.parametrize('w,h,ver', [(16, 16, 2), (48, 32, 1), (256, 16, 1), (1024, 64, 2), (512, 48, 2), (272, 32, 1)])
+def test_edge_geometries(w, h, ver):
+    """Smallest picture, one-macroblock-wide / -high pictures, Width == Stride for all three strides (row wrap of the
+    reference's flat addressing), and the first width past a stride boundary."""
+    from mobiclipdecoder_b200 import SynthParams, SynthStream
+    s = SynthStream(SynthParams(w, h, ver, 99, gop=5, p_intra_mb=0.2, p_split=0.5, p_oob_mv=0.3, p_cbp=0.5))
+    dec, ora = MobiclipDecoder(w, h, ver), Oracle(w, h, ver)
+    for i in range(12):
+        data, key = s.next_frame()
+        dec.Data, dec.Offset = data, 0
+        bmp = dec.DecodeFrame()
+        ok, off, want = ora.decode(data, 0)
+        assert ok and bmp is not None, dec.last_error()
+        assert dec.Offset == off
+        assert np.array_equal(dec.Y[0], ora.y), 'frame %d luma: %s' % (i, _diff_report(dec.Y[0], ora.y, dec.Stride))
+        assert np.array_equal(dec.UV[0], ora.uv), 'frame %d chroma: %s' % (i, _diff_report(dec.UV[0], ora.uv, dec.Stride))
+        assert np.array_equal(bmp, want)
+    dec.close()
+
+
+def test_pipelined_submit_fetch_matches_oracle():
+    name, n_streams, n_frames = 'moflex_400x240', 8, 10
+    w, h, ver, _ = CONFIGS[name]
+    streams = [frames(name, 300 + s, n_frames, gop=4) for s in range(n_streams)]
+    oracles = [Oracle(w, h, ver) for _ in range(n_streams)]
+    want = []
+    for f in range(n_frames):
+        row = []
+        for s in range(n_streams):
+            ok, _, bg = oracles[s].decode(streams[s][f][0], 0, True)
+            assert ok
+            row.append((oracles[s].i420(), bg))
+        want.append(row)
+    for fmt in (MobiBatch.OUT_I420, MobiBatch.OUT_BGRA):
+        b = MobiBatch(w, h, ver, n_streams, n_threads=3)
+        packed = [b.pack_inputs([streams[s][f][0] for s in range(n_streams)]) for f in range(n_frames)]
+        got = []
+        b.submit(packed[0], fmt=fmt)
+        for f in range(1, n_frames):
+            b.submit(packed[f], fmt=fmt)
+            got.append(b.fetch())
+        got.append(b.fetch())
+        for f in range(n_frames):
+            for s in range(n_streams):
+                ref = want[f][s][0] if fmt == MobiBatch.OUT_I420 else want[f][s][1].ravel()
+                assert np.array_equal(got[f][s], ref), 'fmt %d frame %d stream %d' % (fmt, f, s)
+        with pytest.raises(Exception):
+            b.fetch()   # nothing outstanding
+        b.close()
