@@ -202,7 +202,7 @@ __device__ __forceinline__ uint32_t tile_px(const uint8_t* t, int pitch, int pha
 }
 
 template <int LOG2S>
-__global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DevJob* __restrict__ jobs, int mbw, int H,
+__global__ void __launch_bounds__(INTER_WARPS * 32, 7) k_inter(const DevJob* __restrict__ jobs, int mbw, uint32_t mbw_magic, int H,
                                                            const __grid_constant__ CUtensorMap tm_l, const __grid_constant__ CUtensorMap tm_c) {
     __shared__ __align__(128) InterSmem s_all[INTER_WARPS];
     constexpr int S = 1 << LOG2S;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(INTER_WARPS * 32) k_inter(const DevJob* __rest
     }
     const int n_parts = (int)((d.x >> 2) & 127u), n_coef = (int)((d.x >> 9) & 511u);
     const uint32_t blkmask = (d.x >> 18) & 63u;
-    const int mbx = (int)(mb % (uint32_t)mbw), mby = (int)(mb / (uint32_t)mbw);
+    const int mby = (int)__umulhi(mb, mbw_magic), mbx = (int)mb - mby * mbw;   // exact for mb < 2^26 (magic = ceil(2^32 / mbw))
     const size_t ysz = (size_t)S * H;
     const int yoff = ((mby * 16) << LOG2S) + mbx * 16, coff = yoff >> 1;
     const int lrow = lane >> 1, lhalf = lane & 1;
@@ -777,9 +777,10 @@ __global__ void __launch_bounds__(256) k_pack_i420(const uint8_t* const* __restr
 cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, cudaStream_t st) {
     if (n_jobs <= 0) return cudaSuccess;
     dim3 grid((unsigned)((g.mbw * g.mbh + INTER_WARPS - 1) / INTER_WARPS), (unsigned)n_jobs);
-    if (g.log2S == 8) k_inter<8><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, g.H, tm_l, tm_c);
-    else if (g.log2S == 9) k_inter<9><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, g.H, tm_l, tm_c);
-    else k_inter<10><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, g.H, tm_l, tm_c);
+    const uint32_t magic = (uint32_t)((0x100000000ull + (uint64_t)g.mbw - 1) / (uint64_t)g.mbw);
+    if (g.log2S == 8) k_inter<8><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
+    else if (g.log2S == 9) k_inter<9><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
+    else k_inter<10><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
     return cudaGetLastError();
 }
 
