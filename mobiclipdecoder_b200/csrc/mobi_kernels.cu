@@ -618,97 +618,161 @@ __device__ __forceinline__ void intra_residual(uint8_t* t, int ts, int32_t* cb, 
     __syncwarp();
 }
 
+// One intra macroblock, in two halves around the wait for its neighbours.
+struct IntraItem { uint32_t job, m, info, first_op, first_coef, wait; };
+__device__ __forceinline__ IntraItem load_item(const IntraWork* w) {
+    const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(w));
+    const uint2 w1 = __ldg(reinterpret_cast<const uint2*>(w) + 2);
+    return IntraItem{w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
+}
+// Everything that does not depend on neighbouring macroblocks: the op list (returned, one op per lane), the
+// coefficient records and the picture's scale table into shared memory, zeroed tiles.
+__device__ __forceinline__ uint32_t intra_prefetch(const DevJob& J, IntraSmem& sm, const IntraItem& it, int lane) {
+    const int n_ops = (int)((it.info >> 2) & 127u), n_coef = (int)((it.info >> 9) & 511u);
+    const uint32_t myop = lane < n_ops ? __ldg(J.ops + it.first_op + lane) : 0u;
+    const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs) + it.first_coef;
+    for (int i = lane; i < n_coef; i += 32) sm.cf[i] = __ldg(cf + i);
+    const uint32_t* qt = J.hdr->qtab;
+    for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
+    uint4* z = reinterpret_cast<uint4*>(&sm.y[0][0]);  // y and c tiles are contiguous: 832 B = 52 x 16
+    for (int i = lane; i < 52; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+    return myop;
+}
+// Stage the neighbourhood, run the ops in stream order on the tiles, write the macroblock out.
+__device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g, IntraSmem& sm, const IntraItem& it, uint32_t myop, int lane) {
+    const int S = g.S;
+    const uint32_t m = it.m;
+    const int n_ops = (int)((it.info >> 2) & 127u), n_coef = (int)((it.info >> 9) & 511u);
+    const int mbx = (int)(m % (uint32_t)g.mbw), mby = (int)(m / (uint32_t)g.mbw);
+    const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
+    // One round of independent aligned word loads.  luma: 7 words of row y-1 (columns x-4..x+23), then columns
+    // x-4..x-1 of rows y..y+15; when the picture is as wide as the stride the columns right of the last macroblock
+    // wrap onto real pixels of the next row, so the right-hand run x+16..x+23 of rows y..y+15 is staged too (otherwise
+    // it is zero: not yet decoded / padding).
+    const bool wrap = g.W == S && mbx == g.mbw - 1;
+    for (int i = lane; i < 45 + (wrap ? 32 : 0); i += 32) {
+        if (i < 7) *reinterpret_cast<uint32_t*>(&sm.y[0][4 * i]) = nb_luma4(J, g, yoff - S - 4 + 4 * i, m);
+        else if (i < 23) *reinterpret_cast<uint32_t*>(&sm.y[i - 6][0]) = nb_luma4(J, g, yoff + (i - 7) * S - 4, m);
+        else if (i < 45) {
+            const int k = i - 23, p = k / 11, q = k % 11, base = coff + (p ? (S >> 1) : 0);
+            if (q < 3) *reinterpret_cast<uint32_t*>(&sm.c[p][0][4 * q]) = nb_chroma4(J, g, base - S - 4 + 4 * q, m);
+            else *reinterpret_cast<uint32_t*>(&sm.c[p][q - 2][0]) = nb_chroma4(J, g, base + (q - 3) * S - 4, m);
+        } else {
+            const int k = i - 45, r = k >> 1, h = k & 1;
+            *reinterpret_cast<uint32_t*>(&sm.y[1 + r][20 + 4 * h]) = nb_luma4(J, g, yoff + r * S + 16 + 4 * h, m);
+        }
+    }
+    __syncwarp();
+
+    uint32_t cursor = 0;
+    for (int k = 0; k < n_ops; k++) {
+        const uint32_t op = __shfl_sync(0xffffffffu, myop, k);
+        const int mode = (int)(op & 31u), plane = (int)((op >> 6) & 3u), x4 = (int)((op >> 8) & 3u), y4 = (int)((op >> 10) & 3u);
+        const bool res = (op >> 5) & 1u;
+        const int delta = (int)(int16_t)(op >> 16);
+        uint8_t* tp; int ts, off;
+        if (plane == 0) { ts = 32; tp = &sm.y[1 + y4 * 4][4 + x4 * 4]; off = yoff + y4 * 4 * S + x4 * 4; }
+        else { ts = 16; tp = &sm.c[plane - 1][1 + y4 * 4][4 + x4 * 4]; off = coff + (plane == 2 ? (S >> 1) : 0) + y4 * 4 * S + x4 * 4; }
+        const bool left_av = ((off - (plane == 2 ? (S >> 1) : 0)) & (S - 1)) != 0;  // MD:1923, VOffsetfix MD:1885
+        const bool top_av = off >= S;                                               // MD:1924
+        if (mode == 20) intra_predict<16>(tp, ts, 2, delta, left_av, top_av, lane);
+        else if (mode >= 10) {
+            if (mode != 19) intra_predict<4>(tp, ts, mode - 10, delta, left_av, top_av, lane);
+            if (res) intra_residual<4>(tp, ts, sm.coef, sm.qtab, sm.cf, cursor, (uint32_t)n_coef, lane);
+        } else {
+            if (mode != 9) intra_predict<8>(tp, ts, mode, delta, left_av, top_av, lane);
+            if (res) intra_residual<8>(tp, ts, sm.coef, sm.qtab, sm.cf, cursor, (uint32_t)n_coef, lane);
+        }
+    }
+    // write the macroblock out
+    const int lrow = lane >> 1, lhalf = lane & 1;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.y[1 + lrow][4 + lhalf * 8]);
+    *reinterpret_cast<uint2*>(J.dst + yoff + lrow * S + lhalf * 8) = make_uint2(src[0], src[1]);
+    const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1;
+    const uint32_t cv = *reinterpret_cast<const uint32_t*>(&sm.c[cpl][1 + crow][4 + chalf * 4]);
+    *reinterpret_cast<uint32_t*>(J.dst + (size_t)S * g.H + coff + (cpl ? (S >> 1) : 0) + crow * S + chalf * 4) = cv;
+}
+
+// Scattered intra macroblocks (those inside P-pictures): persistent warps draw tickets from a dependency-depth-ordered
+// list; completion is published as a per-macroblock stamp in global memory.
 __global__ void __launch_bounds__(INTRA_WARPS * 32) k_intra(const DevJob* __restrict__ jobs, const IntraWork* __restrict__ work, uint32_t n_work,
                                                            uint32_t* ticket, uint32_t ticket_base, uint32_t stamp, Geom g) {
     __shared__ __align__(16) IntraSmem s_all[INTRA_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     IntraSmem& sm = s_all[warp];
-    const int S = g.S;
     for (;;) {
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(ticket, 1u) - ticket_base;
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_work) break;
-        const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(work + t));
-        const uint2 w1 = __ldg(reinterpret_cast<const uint2*>(work + t) + 2);
-        const DevJob& J = jobs[w0.x];
-        const uint32_t m = w0.y, info = w0.z;
-        const int n_ops = (int)((info >> 2) & 127u), n_coef = (int)((info >> 9) & 511u);
-        const int mbx = (int)(m % (uint32_t)g.mbw), mby = (int)(m / (uint32_t)g.mbw);
-        const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
-
-        // ---- everything that does not depend on neighbouring macroblocks is fetched before the wait ----
-        const uint32_t myop = lane < n_ops ? __ldg(J.ops + w0.w + lane) : 0u;
-        {
-            const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs) + w1.x;
-            for (int i = lane; i < n_coef; i += 32) sm.cf[i] = __ldg(cf + i);
-            const uint32_t* qt = J.hdr->qtab;
-            for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
-            uint4* z = reinterpret_cast<uint4*>(&sm.y[0][0]);  // y and c tiles are contiguous: 832 B = 52 x 16
-            for (int i = lane; i < 52; i += 32) z[i] = make_uint4(0, 0, 0, 0);
-        }
-
-        // ---- wait for the intra neighbours whose pixels this macroblock's predictors read (host-computed mask) ----
-        if (lane < 4 && ((w1.y >> lane) & 1u)) {
-            const int nb = lane == 0 ? (int)m - 1 : (int)m - g.mbw - 2 + lane;
-            volatile uint32_t* f = J.flags + nb;
-            while (*f != stamp) __nanosleep(20);
-        }
-        __syncwarp();
-        __threadfence();
-
-        // ---- stage the neighbourhood: one round of independent aligned word loads ----
-        // luma: 7 words of row y-1 (columns x-4..x+23), then columns x-4..x-1 of rows y..y+15; when the picture is as
-        // wide as the stride the columns right of the last macroblock wrap onto real pixels of the next row, so the
-        // right-hand run x+16..x+23 of rows y..y+15 is staged too (otherwise it is zero: not yet decoded / padding).
-        const bool wrap = g.W == S && mbx == g.mbw - 1;
-        for (int i = lane; i < 45 + (wrap ? 32 : 0); i += 32) {
-            if (i < 7) *reinterpret_cast<uint32_t*>(&sm.y[0][4 * i]) = nb_luma4(J, g, yoff - S - 4 + 4 * i, m);
-            else if (i < 23) *reinterpret_cast<uint32_t*>(&sm.y[i - 6][0]) = nb_luma4(J, g, yoff + (i - 7) * S - 4, m);
-            else if (i < 45) {
-                const int k = i - 23, p = k / 11, q = k % 11, base = coff + (p ? (S >> 1) : 0);
-                if (q < 3) *reinterpret_cast<uint32_t*>(&sm.c[p][0][4 * q]) = nb_chroma4(J, g, base - S - 4 + 4 * q, m);
-                else *reinterpret_cast<uint32_t*>(&sm.c[p][q - 2][0]) = nb_chroma4(J, g, base + (q - 3) * S - 4, m);
-            } else {
-                const int k = i - 45, r = k >> 1, h = k & 1;
-                *reinterpret_cast<uint32_t*>(&sm.y[1 + r][20 + 4 * h]) = nb_luma4(J, g, yoff + r * S + 16 + 4 * h, m);
+        const IntraItem it = load_item(work + t);
+        const DevJob& J = jobs[it.job];
+        const uint32_t myop = intra_prefetch(J, sm, it, lane);
+        // wait for the intra neighbours whose pixels this macroblock's predictors read (host-computed mask)
+        if (lane < 4 && ((it.wait >> lane) & 1u)) {
+            const int nb = lane == 0 ? (int)it.m - 1 : (int)it.m - g.mbw - 2 + lane;
+            // acquire: the neighbour's pixel stores (released below) are visible once its stamp is
+            const uint32_t* f = J.flags + nb;
+            uint32_t seen;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+                if (seen == stamp) break;
+                __nanosleep(20);
             }
         }
         __syncwarp();
+        intra_reconstruct(J, g, sm, it, myop, lane);
+        // release: every lane's pixel stores happen-before the stamp (bar.warp.sync orders the lanes' stores before
+        // lane 0's release at gpu scope through cumulativity)
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(J.flags + it.m), "r"(stamp) : "memory");
+    }
+}
 
-        uint32_t cursor = 0;
-        for (int k = 0; k < n_ops; k++) {
-            const uint32_t op = __shfl_sync(0xffffffffu, myop, k);
-            const int mode = (int)(op & 31u), plane = (int)((op >> 6) & 3u), x4 = (int)((op >> 8) & 3u), y4 = (int)((op >> 10) & 3u);
-            const bool res = (op >> 5) & 1u;
-            const int delta = (int)(int16_t)(op >> 16);
-            uint8_t* tp; int ts, off;
-            if (plane == 0) { ts = 32; tp = &sm.y[1 + y4 * 4][4 + x4 * 4]; off = yoff + y4 * 4 * S + x4 * 4; }
-            else { ts = 16; tp = &sm.c[plane - 1][1 + y4 * 4][4 + x4 * 4]; off = coff + (plane == 2 ? (S >> 1) : 0) + y4 * 4 * S + x4 * 4; }
-            const bool left_av = ((off - (plane == 2 ? (S >> 1) : 0)) & (S - 1)) != 0;  // MD:1923, VOffsetfix MD:1885
-            const bool top_av = off >= S;                                               // MD:1924
-            if (mode == 20) intra_predict<16>(tp, ts, 2, delta, left_av, top_av, lane);
-            else if (mode >= 10) {
-                if (mode != 19) intra_predict<4>(tp, ts, mode - 10, delta, left_av, top_av, lane);
-                if (res) intra_residual<4>(tp, ts, sm.coef, sm.qtab, sm.cf, cursor, (uint32_t)n_coef, lane);
-            } else {
-                if (mode != 9) intra_predict<8>(tp, ts, mode, delta, left_av, top_av, lane);
-                if (res) intra_residual<8>(tp, ts, sm.coef, sm.qtab, sm.cf, cursor, (uint32_t)n_coef, lane);
+// I-pictures: one CTA per picture, one warp per macroblock row (warp w takes rows w, w + KEY_WARPS, ...), macroblocks of
+// a row left to right.  The left neighbour is the warp's own previous macroblock; the rows above are awaited through
+// per-row progress counters in shared memory, so the wavefront's per-level latency is the macroblock's own work plus one
+// L2 round trip for the neighbour pixels -- no flag traffic through L2.  All rows of a picture live in one CTA, so every
+// awaited row is resident: no deadlock.
+constexpr int KEY_WARPS = 16;
+struct KeyPic { uint32_t job, work_base; };
+__global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __restrict__ jobs, const IntraWork* __restrict__ work,
+                                                              const KeyPic* __restrict__ pics, Geom g) {
+    __shared__ __align__(16) IntraSmem s_all[KEY_WARPS];
+    __shared__ volatile uint32_t s_prog[64];   // macroblocks finished per macroblock row (H <= 1024)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 64) s_prog[threadIdx.x] = 0;
+    __syncthreads();
+    IntraSmem& sm = s_all[warp];
+    const KeyPic pic = pics[blockIdx.x];
+    const DevJob& J = jobs[pic.job];
+    const IntraWork* items = work + pic.work_base;   // raster order: every macroblock of an I-picture is intra
+    const int mbw = g.mbw;
+    for (int row = warp; row < g.mbh; row += KEY_WARPS) {
+        for (int x = 0; x < mbw; x++) {
+            const IntraItem it = load_item(items + row * mbw + x);
+            const uint32_t myop = intra_prefetch(J, sm, it, lane);
+            if (lane == 0 && row > 0 && it.wait) {
+                // neighbours by raster index (SURVEY.md 8a hazard 2): left of column 0 = last macroblock of the row above
+                // (bit 0), top-left of column 0 = last macroblock two rows up (bit 1); top-right of the last column is
+                // this row's first macroblock, which this warp finished long ago.
+                uint32_t need1 = 0, need2 = 0;   // progress required of row-1 / row-2
+                if (it.wait & 1u) { if (x == 0) need1 = (uint32_t)mbw; }
+                if (it.wait & 2u) { if (x == 0) need2 = (uint32_t)mbw; else need1 = max(need1, (uint32_t)x); }
+                if (it.wait & 4u) need1 = max(need1, (uint32_t)x + 1u);
+                if ((it.wait & 8u) && x + 1 < mbw) need1 = max(need1, (uint32_t)x + 2u);
+                while (s_prog[row - 1] < need1) __nanosleep(20);
+                if (need2 && row > 1) while (s_prog[row - 2] < need2) __nanosleep(20);
+                __threadfence();
+            }
+            __syncwarp();
+            intra_reconstruct(J, g, sm, it, myop, lane);
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();            // the row's pixels are in L2 before the counter moves
+                s_prog[row] = (uint32_t)x + 1u;
             }
         }
-
-        // write the macroblock out
-        {
-            const int lrow = lane >> 1, lhalf = lane & 1;
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.y[1 + lrow][4 + lhalf * 8]);
-            *reinterpret_cast<uint2*>(J.dst + yoff + lrow * S + lhalf * 8) = make_uint2(src[0], src[1]);
-            const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1;
-            const uint32_t cv = *reinterpret_cast<const uint32_t*>(&sm.c[cpl][1 + crow][4 + chalf * 4]);
-            *reinterpret_cast<uint32_t*>(J.dst + (size_t)S * g.H + coff + (cpl ? (S >> 1) : 0) + crow * S + chalf * 4) = cv;
-        }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) *(volatile uint32_t*)(J.flags + m) = stamp;
     }
 }
 
@@ -796,6 +860,12 @@ cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_w
     if (blocks > cap) blocks = cap;
     k_intra<<<blocks, INTRA_WARPS * 32, 0, st>>>(jobs, work, n_work, ticket, ticket_base, stamp, g);
     *warps_launched = blocks * INTRA_WARPS;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_intra_key(const DevJob* jobs, const IntraWork* work, const void* pics, int n_pics, Geom g, cudaStream_t st) {
+    if (n_pics <= 0) return cudaSuccess;
+    k_intra_key<<<(unsigned)n_pics, KEY_WARPS * 32, 0, st>>>(jobs, work, reinterpret_cast<const KeyPic*>(pics), g);
     return cudaGetLastError();
 }
 

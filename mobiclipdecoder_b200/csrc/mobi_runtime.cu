@@ -104,7 +104,7 @@ struct Arena {
 // Where one step's arrays live on the device, plus the host-side facts needed to launch it again.
 struct StepLayout {
     size_t bytes = 0;
-    size_t jobs_off = 0, work_off = 0;
+    size_t jobs_off = 0, work_off = 0, key_off = 0;   // job table, intra work list, {job, work_base} of the I-pictures
     int n_jobs = 0, n_inter_jobs = 0, n_key_jobs = 0;
     uint32_t n_work = 0;      // all intra macroblocks; the list holds those of P-pictures first, then those of I-pictures
     uint32_t n_work_p = 0;    // intra macroblocks inside P-pictures
@@ -571,6 +571,7 @@ private:
             L.parts += h.n_parts; L.coefs += h.n_coefs; L.ops += h.n_ops; L.inter_coefs += h.n_inter_coefs;
         }
         L.work_off = p; p = align_up(p + sizeof(IntraWork) * L.n_work, 256);
+        L.key_off = p; p = align_up(p + 8 * (size_t)L.n_jobs, 256);
         for (int j = 0; j < L.n_jobs; j++) {
             const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr;
             Off& o = off[j];
@@ -648,30 +649,35 @@ private:
                 const uint16_t* per_rank = depth_[j].data() + h.n_mb;
                 for (uint32_t r = 0; r < h.n_intra; r++) if (per_rank[2 * r] > maxd) maxd = per_rank[2 * r];
             }
-            bucket_.assign(2 * ((size_t)maxd + 2), 0);  // [list][depth]
-            uint32_t* cnt[2] = {bucket_.data(), bucket_.data() + maxd + 2};
+            // P-pictures' intra macroblocks: counting sort by depth.  I-pictures: raster order per picture (the row kernel
+            // indexes work[work_base + m]), pictures one after the other behind the P list.
+            bucket_.assign((size_t)maxd + 2, 0);
+            uint32_t* cnt = bucket_.data();
             for (int j = 0; j < L.n_jobs; j++) {
                 const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr;
-                const int list = h.n_intra == h.n_mb ? 1 : 0;
-                if (list) L.n_key_jobs++; else L.n_work_p += h.n_intra;
+                if (h.n_intra == h.n_mb) { L.n_key_jobs++; continue; }
+                L.n_work_p += h.n_intra;
                 const uint16_t* per_rank = depth_[j].data() + h.n_mb;
-                for (uint32_t r = 0; r < h.n_intra; r++) cnt[list][per_rank[2 * r]]++;
+                for (uint32_t r = 0; r < h.n_intra; r++) cnt[per_rank[2 * r]]++;
             }
             uint32_t at = 0;
-            for (int list = 0; list < 2; list++)
-                for (uint32_t dd = 0; dd <= maxd + 1; dd++) { const uint32_t c = cnt[list][dd]; cnt[list][dd] = at; at += c; }
+            for (uint32_t dd = 0; dd <= maxd + 1; dd++) { const uint32_t c = cnt[dd]; cnt[dd] = at; at += c; }
+            uint32_t key_at = L.n_work_p, n_key = 0;
+            uint32_t* keytab = reinterpret_cast<uint32_t*>(a.h + L.key_off);
             for (int j = 0; j < L.n_jobs; j++) {
                 const mobi_packed_frame& f = views_[L.job_stream[j]];
                 const mobi_frame_hdr& h = *f.hdr;
-                const int list = h.n_intra == h.n_mb ? 1 : 0;
+                const bool key = h.n_intra == h.n_mb;
                 const uint16_t* per_rank = depth_[j].data() + h.n_mb;
+                if (key) { keytab[2 * n_key] = (uint32_t)j; keytab[2 * n_key + 1] = key_at; n_key++; }
                 for (uint32_t r = 0; r < h.n_intra; r++) {
                     const uint32_t m = f.intra_list[r];
                     const mobi_mb& mb = f.mbs[m];
-                    IntraWork& w = work[cnt[list][per_rank[2 * r]]++];
+                    IntraWork& w = work[key ? key_at + r : cnt[per_rank[2 * r]]++];
                     w.job = (uint32_t)j; w.mb = m; w.info = mb.info; w.first_op = mb.first_sub; w.first_coef = mb.first_coef;
                     w.wait = per_rank[2 * r + 1]; w.pad[0] = w.pad[1] = 0;
                 }
+                if (key) key_at += h.n_intra;
             }
         }
         return MOBI_OK;
@@ -696,15 +702,12 @@ private:
         stamp_++;
         if (n_key) {
             // I-pictures: long dependency chains, little parallelism (about mbw/2 macroblocks per picture at a time).
-            // A few warps per picture on the side stream, concurrent with this step's inter kernel.
+            // One CTA per picture on the side stream, concurrent with this step's inter kernel.
             if (!ok(cudaEventRecord(fork_, stream_), "cudaEventRecord")) return MOBI_ERR_CUDA;
             if (!ok(cudaStreamWaitEvent(side_, fork_, 0), "cudaStreamWaitEvent")) return MOBI_ERR_CUDA;
-            uint32_t warps = 0;
-            const uint32_t want = (uint32_t)L.n_key_jobs * (uint32_t)(g_.mbw < 8 ? 8 : g_.mbw);
             if (timing_) tick(2, side_);
-            if (!ok(launch_intra(jobs, work + L.n_work_p, n_key, ticket_ + 32, ticket_base_[1], stamp_, g_, want, side_, &warps), "k_intra(I)")) return MOBI_ERR_CUDA;
+            if (!ok(launch_intra_key(jobs, work, d + L.key_off, L.n_key_jobs, g_, side_), "k_intra_key")) return MOBI_ERR_CUDA;
             if (timing_) tick(2, side_);
-            ticket_base_[1] += n_key + warps;  // every warp draws exactly one ticket past the end
             stats_.launches++;
             if (!ok(cudaEventRecord(join_, side_), "cudaEventRecord")) return MOBI_ERR_CUDA;
         }
@@ -744,7 +747,8 @@ private:
             if (kind == 1) {
                 if (nsub > 32) return set_err(MOBI_ERR_ARG, "packed frame: MB %u has more intra ops than any macroblock can (27)", m);
                 if ((uint64_t)mb.first_sub + nsub > h.n_ops) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op range", m);
-                if (mb.intra_rank >= h.n_intra || f.intra_list[mb.intra_rank] != m) return set_err(MOBI_ERR_ARG, "packed frame: MB %u intra rank", m);
+                if (mb.intra_rank != n_intra || mb.intra_rank >= h.n_intra || f.intra_list[mb.intra_rank] != m)   // ranks ascend in raster order
+                    return set_err(MOBI_ERR_ARG, "packed frame: MB %u intra rank", m);
                 n_intra++;
                 continue;
             }
