@@ -75,6 +75,30 @@ MOBICUDA_EXPORTS = {
 }
 
 
+class ModsHeader(C.Structure):
+    _fields_ = [('magic', C.c_char * 4), ('tag_id', C.c_uint16), ('tag_id_size_dword', C.c_uint16), ('frame_count', C.c_uint32),
+                ('width', C.c_uint32), ('height', C.c_uint32), ('fps', C.c_uint32), ('audio_codec', C.c_uint16), ('nb_channel', C.c_uint16),
+                ('frequency', C.c_uint32), ('biggest_frame', C.c_uint32), ('audio_offset', C.c_uint32), ('keyframe_index_offset', C.c_uint32),
+                ('keyframe_count', C.c_uint32)]
+
+
+class Moc5Info(C.Structure):
+    _fields_ = [('width', C.c_uint32), ('height', C.c_uint32), ('fps_x128', C.c_uint32), ('first_block', C.c_uint32)]
+
+
+# every symbol include/mobidemux.h declares (same library)
+MOBIDEMUX_EXPORTS = {
+    'mobi_mods_open': (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    'mobi_mods_close': (None, [C.c_void_p]),
+    'mobi_mods_get_header': (C.c_int, [C.c_void_p, C.POINTER(ModsHeader)]),
+    'mobi_mods_keyframe': (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    'mobi_mods_read_frame': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]),
+    'mobi_mods_jump_to_keyframe': (C.c_int, [C.c_void_p, C.c_uint32]),
+    'mobi_moc5_open': (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(Moc5Info)]),
+    'mobi_moc5_next': (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+}
+
+
 class SynthParamsC(C.Structure):
     _fields_ = [('width', C.c_uint32), ('height', C.c_uint32), ('version', C.c_int32), ('seed', C.c_uint64), ('gop', C.c_int32),
                 ('quant', C.c_int32), ('p_dquant', C.c_float), ('p_split', C.c_float), ('p_intra_mb', C.c_float), ('p_sub_mb', C.c_float),
@@ -116,7 +140,7 @@ def _load(name, exports):
 
 
 def mobicuda():
-    return _load('libmobicuda.so', MOBICUDA_EXPORTS)
+    return _load('libmobicuda.so', dict(MOBICUDA_EXPORTS, **MOBIDEMUX_EXPORTS))
 
 
 def mobisynth():

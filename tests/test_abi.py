@@ -62,3 +62,13 @@ def test_product_library_does_not_link_the_oracle():
         if f.endswith('.py'):
             text = open(os.path.join(ROOT, 'mobiclipdecoder_b200', f)).read()
             assert 'oracle_lib' not in text and 'libmobioracle' not in text.replace("'oracle', '_build'", '') or f == '_build.py'
+
+
+def test_mobidemux_exports_match_header():
+    decl = _declared('mobidemux.h')
+    lib = C.CDLL(os.path.join(ROOT, 'mobiclipdecoder_b200', 'lib', 'libmobicuda.so'))
+    for name, nargs in decl.items():
+        assert hasattr(lib, name), 'libmobicuda.so does not export %s' % name
+        assert len(_native.MOBIDEMUX_EXPORTS[name][1]) == nargs
+    assert set(_native.MOBIDEMUX_EXPORTS) == set(decl)
+    assert C.sizeof(_native.ModsHeader) == 0x30
