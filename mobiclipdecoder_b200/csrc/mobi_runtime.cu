@@ -18,6 +18,7 @@
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -193,6 +194,7 @@ public:
         if (!ok(cudaMalloc(&ptr_d_, sizeof(void*) * (size_t)N_), "cudaMalloc(ptrs)")) return MOBI_ERR_NOMEM;
         if (!ok(cudaMallocHost(&ptr_h_, sizeof(void*) * (size_t)N_), "cudaMallocHost(ptrs)")) return MOBI_ERR_NOMEM;
         if (!ok(cudaStreamSynchronize(stream_), "init sync")) return MOBI_ERR_CUDA;
+        if (const char* e = std::getenv("MOBI_INTER_KERNEL")) pipelined_ = std::strcmp(e, "pipe") == 0;
         return make_tensor_maps();
     }
     // The ring as one rank-3 u8 tensor (Stride, 1.5*H, pictures): a picture's chroma rows follow its luma rows at the
@@ -713,7 +715,7 @@ private:
         }
         if (L.n_inter_jobs) {
             if (timing_) tick(0, stream_);
-            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_l_, tm_c_, stream_), "k_inter")) return MOBI_ERR_CUDA;
+            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_l_, tm_c_, pipelined_, stream_), "k_inter")) return MOBI_ERR_CUDA;
             if (timing_) tick(0, stream_);
             stats_.launches++;
         }
@@ -810,6 +812,7 @@ private:
     uint32_t* ticket_ = nullptr;
     uint32_t ticket_base_[2] = {0, 0}, stamp_ = 0;
     CUtensorMap tm_l_, tm_c_;
+    bool pipelined_ = false;  // MOBI_INTER_KERNEL=pipe selects k_inter_pipe (one warp per run of 16 macroblocks; measured slower)
     cudaStream_t side_ = nullptr;
     cudaEvent_t fork_ = nullptr, join_ = nullptr;
     std::vector<std::vector<uint16_t>> depth_;
