@@ -81,7 +81,8 @@ struct FrameParse {
     uint32_t cur_deps = 0;
     int cur_mbx = 0, cur_mby = 0;
 
-    FrameParse(Parser& p, ParsedFrame& o) : P(p), out(o), S(p.S_), W((int)p.W_), H((int)p.H_) {}
+    int log2S;
+    FrameParse(Parser& p, ParsedFrame& o) : P(p), out(o), S(p.S_), W((int)p.W_), H((int)p.H_), log2S(p.S_ == 256 ? 8 : p.S_ == 512 ? 9 : 10) {}
 
     static uint32_t tab(const uint8_t* t, uint32_t n, uint32_t i) {
         if (i >= n) fail(MOBI_ERR_BITSTREAM, "code index outside table");
@@ -106,67 +107,81 @@ struct FrameParse {
 
     // ReadDCTMatrix MD:3330-3432: emits quantised levels; scaling happens on the device.
     // n = 64 or 16; tag = blk | sub<<... as stored in mobi_coef.
+    // The bit window lives in locals for the duration of the block (the compiler cannot keep members in registers
+    // across the stores to the output array); the refill rule is the reference's, one 16-bit word per check.
     void coefs(int n, uint8_t blk, uint8_t sub, uint32_t& blkmask_any) {
         const uint16_t* A = g_vlc[vlcsel == 1];
         const uint8_t* B = vlcsel == 1 ? MOBI_VLC1_ESC : MOBI_VLC0_ESC;
         const uint32_t* qt = n == 64 ? P.st_.qtab : P.st_.qtab + 64;
+        const bool check_qt = !P.st_.qtab_clean;
+        const uint8_t* const data = b.d;
+        const int len = b.len;
+        uint32_t win = b.win;
+        int nb = b.nb, off = b.off;
+        mobi_coef* dst = &out.coefs.v[out.coefs.n];
+        const uint8_t tag = (uint8_t)(blk | (n == 64 ? 0x80 : 0));
+#define MOBI_CHK() do { if (nb < 0 && off < len) { if (off + 1 >= len) fail(MOBI_ERR_BITSTREAM, "read past end of frame data"); \
+                                                    const uint32_t w_ = (uint32_t)data[off] | (uint32_t)data[off + 1] << 8; off += 2; nb += 16; win |= w_ << ((16 - nb) & 31); } } while (0)
         uint32_t pos = 0;
         for (;;) {
             int run, level, nbits;
             uint32_t e, last;
-            if ((b.win >> 25) == 3) {
-                b.win <<= 7;
-                uint32_t c = b.win >> 31; b.win <<= 1;
+            if (__builtin_expect((win >> 25) == 3, 0)) {
+                win <<= 7;
+                uint32_t c = win >> 31; win <<= 1;
                 if (!c) {
-                    b.nb -= 8; b.chk();
-                    e = A[b.win >> 20];
+                    nb -= 8; MOBI_CHK();
+                    e = A[win >> 20];
                     int add = B[e >> 9];
                     nbits = e & 15; e >>= 4; level = (int)(e & 31) + add; e >>= 5;
-                    b.win <<= ((nbits - 1) & 31);
-                    if (b.win >> 31) level = -level;
-                    b.win <<= 1; b.nb -= nbits; b.chk();
+                    win <<= ((nbits - 1) & 31);
+                    if (win >> 31) level = -level;
+                    win <<= 1; nb -= nbits; MOBI_CHK();
                     run = e & 63; last = e >> 6;
                 } else {
-                    c = b.win >> 31; b.win <<= 1;
+                    c = win >> 31; win <<= 1;
                     if (!c) {
-                        b.nb -= 9; b.chk();
-                        e = A[b.win >> 20];
+                        nb -= 9; MOBI_CHK();
+                        e = A[win >> 20];
                         nbits = e & 15; e >>= 4; level = e & 31; e >>= 5;
                         uint32_t r = e & 63; e >>= 6;
                         int add = B[0x80 + level + (e << 6)];
-                        b.win <<= ((nbits - 1) & 31);
-                        if (b.win >> 31) level = -level;
-                        b.win <<= 1; b.nb -= nbits; b.chk();
+                        win <<= ((nbits - 1) & 31);
+                        if (win >> 31) level = -level;
+                        win <<= 1; nb -= nbits; MOBI_CHK();
                         run = (int)r + add; last = e;
                     } else {
-                        b.nb -= 9; b.chk();
-                        last = b.win >> 31; b.win <<= 1;
-                        run = b.win >> 26; b.win <<= 6;
-                        b.nb -= 7; b.chk();
-                        level = (int32_t)b.win >> 20; b.win <<= 12;
-                        b.nb -= 12; b.chk();
+                        nb -= 9; MOBI_CHK();
+                        last = win >> 31; win <<= 1;
+                        run = win >> 26; win <<= 6;
+                        nb -= 7; MOBI_CHK();
+                        level = (int32_t)win >> 20; win <<= 12;
+                        nb -= 12; MOBI_CHK();
                     }
                 }
             } else {
-                e = A[b.win >> 20];
+                e = A[win >> 20];
                 nbits = e & 15; e >>= 4; level = e & 31; e >>= 5;
-                b.win <<= ((nbits - 1) & 31);
-                if (b.win >> 31) level = -level;
-                b.win <<= 1; b.nb -= nbits; b.chk();
+                win <<= ((nbits - 1) & 31);
+                const int32_t neg = -(int32_t)(win >> 31);          // branch-free sign: 0 or -1
+                level = (level ^ neg) - neg;
+                win <<= 1; nb -= nbits; MOBI_CHK();
                 run = e & 63; last = e >> 6;
             }
             pos += (uint32_t)run;
             // The reference indexes Internal[] with no check: a run past the block walks into the next table.
-            if (pos >= (uint32_t)n) fail(MOBI_ERR_BITSTREAM, "coefficient run past end of block");
-            if (!P.st_.qtab_clean && (qt[pos] & 0xFF) >= 64u) fail(MOBI_ERR_BITSTREAM, "quantiser < 12 corrupts the scan table (MD:3909-3911)");
-            mobi_coef c;
-            c.level = (int16_t)level;
-            c.pos = (uint8_t)(pos | (uint32_t)sub << 6);
-            c.blk = (uint8_t)(blk | (n == 64 ? 0x80 : 0) | ((last & 1) ? 0x40 : 0));
-            out.coefs.push_back(c);
+            if (__builtin_expect(pos >= (uint32_t)n, 0)) fail(MOBI_ERR_BITSTREAM, "coefficient run past end of block");
+            if (check_qt && (qt[pos] & 0xFF) >= 64u) fail(MOBI_ERR_BITSTREAM, "quantiser < 12 corrupts the scan table (MD:3909-3911)");
+            dst->level = (int16_t)level;
+            dst->pos = (uint8_t)(pos | (uint32_t)sub << 6);
+            dst->blk = (uint8_t)(tag | ((last & 1) ? 0x40 : 0));
+            dst++;
             pos++;
             if (last & 1) break;
         }
+#undef MOBI_CHK
+        out.coefs.n = (size_t)(dst - out.coefs.v.data());
+        b.win = win; b.nb = nb; b.off = off;
         blkmask_any |= 1u << (blk & 7);
     }
 
@@ -204,7 +219,7 @@ struct FrameParse {
         case 2: top = left = true; break;
         case 3: {
             const int po = plane == 2 ? off - S / 2 : off;
-            left = (po % S) != 0; top = off >= S;   // MD:1923-1924
+            left = (po & (S - 1)) != 0; top = off >= S;   // MD:1923-1924 (Stride is a power of two, MD:50-52)
             break; }
         case 5: case 6: case 7: top = left = tl = true; break;
         case 8: top = true; ext = N == 8 ? 5 : 4; break;   // T0..12 / two top words (MD:2371-2466, 2737-2746)
@@ -327,7 +342,7 @@ struct FrameParse {
         mobi_mb mb;
         uint32_t first_op = (uint32_t)out.ops.size(), first_coef = (uint32_t)out.coefs.size(), mask = 0;
         cur_deps = 0;
-        cur_mbx = (mboff % S) / 16; cur_mby = (mboff / S) / 16;
+        cur_mbx = (mboff & (S - 1)) >> 4; cur_mby = (mboff >> log2S) >> 4;
         if (sub) intra_sub(mboff, mask); else intra_full(mboff, mask);
         uint32_t nops = (uint32_t)out.ops.size() - first_op, nco = (uint32_t)out.coefs.size() - first_coef;
         mb.info = 1u | nops << 2 | nco << 9 | mask << 18 | cur_deps << 24;
@@ -350,7 +365,7 @@ struct FrameParse {
         long long clast = cfirst + S / 2 + (long long)((h >> 1) - 1 + (cdy & 1)) * S + (w >> 1) - 1 + (cdx & 1);
         if (cfirst < 0 || clast >= (long long)S * H / 2) fail(MOBI_ERR_RANGE, "motion vector reads outside the chroma array");
         if (dx < -32768 || dx > 32767 || dy < -32768 || dy > 32767) fail(MOBI_ERR_RANGE, "motion vector outside 16 bits");
-        int rel = off - mboff, x = rel % S, y = rel / S;
+        int rel = off - mboff, x = rel & (S - 1), y = rel >> log2S;
         mobi_part p;
         p.xy = (uint8_t)((x >> 1) | (y >> 1) << 4);
         p.shape = (uint8_t)(lw | lh << 2 | ref << 4);

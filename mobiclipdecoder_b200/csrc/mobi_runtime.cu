@@ -125,7 +125,7 @@ struct OutSlot {
     const uint8_t** ptr_h = nullptr;
     const uint8_t** ptr_d = nullptr;
     size_t cap = 0, bytes = 0;
-    cudaEvent_t ready = nullptr;
+    cudaEvent_t ready = nullptr, converted = nullptr;
 };
 
 }  // namespace
@@ -160,6 +160,7 @@ public:
             if (ptr_h_) cudaFreeHost(ptr_h_);
             for (int w = 0; w < 3; w++) for (cudaEvent_t e : ev_[w]) cudaEventDestroy(e);
             if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
+            if (copy_) { cudaStreamSynchronize(copy_); cudaStreamDestroy(copy_); }
             if (fork_) cudaEventDestroy(fork_);
             if (join_) cudaEventDestroy(join_);
             for (cudaEvent_t e : ev_free_) cudaEventDestroy(e);
@@ -169,6 +170,7 @@ public:
                 if (o.ptr_h) cudaFreeHost(o.ptr_h);
                 if (o.ptr_d) cudaFree(o.ptr_d);
                 if (o.ready) cudaEventDestroy(o.ready);
+                if (o.converted) cudaEventDestroy(o.converted);
             }
             cudaStreamDestroy(stream_);
         }
@@ -181,6 +183,7 @@ public:
         sm_count_ = prop.multiProcessorCount;
         if (!ok(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return MOBI_ERR_CUDA;
         if (!ok(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking), "cudaStreamCreate")) return MOBI_ERR_CUDA;
+        if (!ok(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking), "cudaStreamCreate")) return MOBI_ERR_CUDA;
         if (!ok(cudaEventCreateWithFlags(&fork_, cudaEventDisableTiming), "cudaEventCreate")) return MOBI_ERR_CUDA;
         if (!ok(cudaEventCreateWithFlags(&join_, cudaEventDisableTiming), "cudaEventCreate")) return MOBI_ERR_CUDA;
         if (!ok(cudaMalloc(&ring_, pic_ * RING * (size_t)N_), "cudaMalloc(ring)")) return MOBI_ERR_NOMEM;
@@ -327,7 +330,8 @@ public:
     }
     int sync() {
         if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
-        return ok(cudaStreamSynchronize(stream_), "cudaStreamSynchronize") ? MOBI_OK : MOBI_ERR_CUDA;
+        if (!ok(cudaStreamSynchronize(stream_), "cudaStreamSynchronize")) return MOBI_ERR_CUDA;
+        return ok(cudaStreamSynchronize(copy_), "cudaStreamSynchronize") ? MOBI_OK : MOBI_ERR_CUDA;
     }
 
     // ---- read-back --------------------------------------------------------------------------------
@@ -439,6 +443,7 @@ public:
             if (!ok(cudaMallocHost(&o.ptr_h, sizeof(void*) * N_), "cudaMallocHost(ptrs)")) return MOBI_ERR_NOMEM;
             if (!ok(cudaMalloc(&o.ptr_d, sizeof(void*) * N_), "cudaMalloc(ptrs)")) return MOBI_ERR_NOMEM;
             if (!ok(cudaEventCreateWithFlags(&o.ready, cudaEventDisableTiming), "cudaEventCreate")) return MOBI_ERR_CUDA;
+            if (!ok(cudaEventCreateWithFlags(&o.converted, cudaEventDisableTiming), "cudaEventCreate")) return MOBI_ERR_CUDA;
         }
         for (int s = 0; s < N_; s++) {
             if (count_[s] == 0) return set_err(MOBI_ERR_STATE, "stream %d: no picture decoded yet", s);
@@ -448,10 +453,13 @@ public:
         if (format == 1) { if (!ok(launch_pack_i420(o.ptr_d, N_, o.d, g_, stream_), "k_pack_i420")) return MOBI_ERR_CUDA; }
         else { if (!ok(launch_bgra(o.ptr_d, N_, o.d, (int)W_ * 4, per, g_, stream_), "k_bgra")) return MOBI_ERR_CUDA; }
         stats_.launches++;
-        if (!ok(cudaMemcpyAsync(o.h, o.d, total, cudaMemcpyDeviceToHost, stream_), "D2H result")) return MOBI_ERR_CUDA;
+        // the copy back runs on its own stream so that it overlaps the upload and the kernels of the next step
+        if (!ok(cudaEventRecord(o.converted, stream_), "cudaEventRecord")) return MOBI_ERR_CUDA;
+        if (!ok(cudaStreamWaitEvent(copy_, o.converted, 0), "cudaStreamWaitEvent")) return MOBI_ERR_CUDA;
+        if (!ok(cudaMemcpyAsync(o.h, o.d, total, cudaMemcpyDeviceToHost, copy_), "D2H result")) return MOBI_ERR_CUDA;
         stats_.d2h_bytes += total;
         stats_.h2d_bytes += sizeof(void*) * N_;
-        if (!ok(cudaEventRecord(o.ready, stream_), "cudaEventRecord")) return MOBI_ERR_CUDA;
+        if (!ok(cudaEventRecord(o.ready, copy_), "cudaEventRecord")) return MOBI_ERR_CUDA;
         o.bytes = total;
         slot_head_ ^= 1;
         slots_used_++;
@@ -813,7 +821,7 @@ private:
     uint32_t ticket_base_[2] = {0, 0}, stamp_ = 0;
     CUtensorMap tm_l_, tm_c_;
     bool pipelined_ = false;  // MOBI_INTER_KERNEL=pipe selects k_inter_pipe (one warp per run of 16 macroblocks; measured slower)
-    cudaStream_t side_ = nullptr;
+    cudaStream_t side_ = nullptr, copy_ = nullptr;
     cudaEvent_t fork_ = nullptr, join_ = nullptr;
     std::vector<std::vector<uint16_t>> depth_;
     std::vector<uint32_t> bucket_;
