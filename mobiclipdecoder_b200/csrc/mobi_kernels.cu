@@ -1013,7 +1013,7 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
 
 // Scattered intra macroblocks (those inside P-pictures): persistent warps draw tickets from a dependency-depth-ordered
 // list; completion is published as a per-macroblock stamp in global memory.
-__global__ void __launch_bounds__(INTRA_WARPS * 32) k_intra(const DevJob* __restrict__ jobs, const IntraWork* __restrict__ work, uint32_t n_work,
+__global__ void __launch_bounds__(INTRA_WARPS * 32, 8) k_intra(const DevJob* __restrict__ jobs, const IntraWork* __restrict__ work, uint32_t n_work,
                                                            uint32_t* ticket, uint32_t ticket_base, uint32_t stamp, Geom g) {
     __shared__ __align__(16) IntraSmem s_all[INTRA_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
