@@ -44,7 +44,10 @@ cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_w
                          uint32_t stamp, Geom g, uint32_t max_warps, cudaStream_t st, uint32_t* warps_launched);
 // I-pictures: one CTA per picture.  pics = device array of n_pics {uint32 job, uint32 work_base}; the picture's work items lie in
 // raster order at work[work_base + m].
-cudaError_t launch_intra_key(const DevJob* jobs, const IntraWork* work, const void* pics, int n_pics, Geom g, cudaStream_t st);
+// Every CTA adds 1 to *resident when it starts (launch_gate waits on that count).
+cudaError_t launch_intra_key(const DevJob* jobs, const IntraWork* work, const void* pics, int n_pics, Geom g, uint32_t* resident, cudaStream_t st);
+// One tiny CTA that returns once *resident has reached target (wrap-safe) or after ~0.2 ms.
+cudaError_t launch_gate(const uint32_t* resident, uint32_t target, cudaStream_t st);
 // Y/UV planes of n pictures -> BGRA (MD:260-323). srcs = device array of luma plane pointers; picture i goes to
 // dst + i*dst_picture_bytes with dst_pitch bytes per row.
 cudaError_t launch_bgra(const uint8_t* const* srcs, int n, uint8_t* dst, int dst_pitch, size_t dst_picture_bytes, Geom g, cudaStream_t st);

@@ -716,10 +716,15 @@ private:
             if (!ok(cudaEventRecord(fork_, stream_), "cudaEventRecord")) return MOBI_ERR_CUDA;
             if (!ok(cudaStreamWaitEvent(side_, fork_, 0), "cudaStreamWaitEvent")) return MOBI_ERR_CUDA;
             if (timing_) tick(2, side_);
-            if (!ok(launch_intra_key(jobs, work, d + L.key_off, L.n_key_jobs, g_, side_), "k_intra_key")) return MOBI_ERR_CUDA;
+            if (!ok(launch_intra_key(jobs, work, d + L.key_off, L.n_key_jobs, g_, ticket_ + 32, side_), "k_intra_key")) return MOBI_ERR_CUDA;
             if (timing_) tick(2, side_);
             stats_.launches++;
             if (!ok(cudaEventRecord(join_, side_), "cudaEventRecord")) return MOBI_ERR_CUDA;
+            key_resident_ += (uint32_t)L.n_key_jobs;
+            if (L.n_inter_jobs) {   // let the few large I-picture CTAs settle before the flood of small k_inter CTAs
+                if (!ok(launch_gate(ticket_ + 32, key_resident_, stream_), "k_gate")) return MOBI_ERR_CUDA;
+                stats_.launches++;
+            }
         }
         if (L.n_inter_jobs) {
             if (timing_) tick(0, stream_);
@@ -818,7 +823,7 @@ private:
     uint8_t* ring_ = nullptr;
     uint32_t* flags_ = nullptr;
     uint32_t* ticket_ = nullptr;
-    uint32_t ticket_base_[2] = {0, 0}, stamp_ = 0;
+    uint32_t ticket_base_[2] = {0, 0}, stamp_ = 0, key_resident_ = 0;
     CUtensorMap tm_l_, tm_c_;
     bool pipelined_ = false;  // MOBI_INTER_KERNEL=pipe selects k_inter_pipe (one warp per run of 16 macroblocks; measured slower)
     cudaStream_t side_ = nullptr, copy_ = nullptr;
