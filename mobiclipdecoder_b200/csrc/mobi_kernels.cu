@@ -22,6 +22,8 @@ namespace mobi {
 namespace {
 
 constexpr int INTER_WARPS = 8;
+// ids of the set bits of a 6-bit coded-block mask, one nibble each, lowest first (slot order of the coefficient buffers)
+__constant__ uint32_t c_blklist[64];
 constexpr int INTRA_WARPS = 4;
 
 // ------------------------------------------------------------------------------------------------
@@ -157,39 +159,40 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
                  :: "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
-// Same arithmetic as mc_row8 / mc_row4 on a box row held in shared memory (row pitch 32); p may have any alignment.
-__device__ __forceinline__ void lds_row8(const uint8_t* p, uint32_t& a0, uint32_t& a1, uint32_t& b0, uint32_t& b1) {
-    const uint32_t ad = smem_u32(p), sh = (ad & 3u) * 8u;
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - (ad & 3u));
+// Same arithmetic as mc_row8 / mc_row4 on a box row held in shared memory (row pitch 32).  base is 4-byte aligned (the
+// boxes are 128-byte aligned), off any byte offset: the misalignment comes from off alone, no address conversion needed.
+__device__ __forceinline__ void lds_row8(const uint8_t* base, uint32_t off, uint32_t& a0, uint32_t& a1, uint32_t& b0, uint32_t& b1) {
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(base + (off & ~3u));
     const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
     a0 = __funnelshift_r(w0, w1, sh); a1 = __funnelshift_r(w1, w2, sh);
     b0 = __funnelshift_rc(w0, w1, sh + 8u); b1 = __funnelshift_rc(w1, w2, sh + 8u);
 }
-__device__ __forceinline__ void tile_row8(const uint8_t* p, int phase, uint32_t& o0, uint32_t& o1) {
+__device__ __forceinline__ void tile_row8(const uint8_t* base, uint32_t off, int phase, uint32_t& o0, uint32_t& o1) {
     uint32_t a0, a1, b0, b1;
-    lds_row8(p, a0, a1, b0, b1);
+    lds_row8(base, off, a0, a1, b0, b1);
     if (phase == 0) { o0 = a0; o1 = a1; return; }
     if (phase == 1) { o0 = half4(a0) + half4(b0); o1 = half4(a1) + half4(b1); return; }
     uint32_t c0, c1, d0, d1;
-    lds_row8(p + 32, c0, c1, d0, d1);
+    lds_row8(base, off + 32u, c0, c1, d0, d1);
     if (phase == 2) { o0 = half4(a0) + half4(c0); o1 = half4(a1) + half4(c1); return; }
     o0 = half4(half4(a0) + half4(b0)) + half4(half4(c0) + half4(d0));
     o1 = half4(half4(a1) + half4(b1)) + half4(half4(c1) + half4(d1));
 }
-__device__ __forceinline__ void lds_row4(const uint8_t* p, uint32_t& a0, uint32_t& b0) {
-    const uint32_t ad = smem_u32(p), sh = (ad & 3u) * 8u;
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(p - (ad & 3u));
+__device__ __forceinline__ void lds_row4(const uint8_t* base, uint32_t off, uint32_t& a0, uint32_t& b0) {
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(base + (off & ~3u));
     const uint32_t w0 = q[0], w1 = q[1];
     a0 = __funnelshift_r(w0, w1, sh);
     b0 = __funnelshift_rc(w0, w1, sh + 8u);
 }
-__device__ __forceinline__ uint32_t tile_row4(const uint8_t* p, int phase) {
+__device__ __forceinline__ uint32_t tile_row4(const uint8_t* base, uint32_t off, int phase) {
     uint32_t a0, b0;
-    lds_row4(p, a0, b0);
+    lds_row4(base, off, a0, b0);
     if (phase == 0) return a0;
     if (phase == 1) return half4(a0) + half4(b0);
     uint32_t c0, d0;
-    lds_row4(p + 32, c0, d0);
+    lds_row4(base, off + 32u, c0, d0);
     if (phase == 2) return half4(a0) + half4(c0);
     return half4(half4(a0) + half4(b0)) + half4(half4(c0) + half4(d0));
 }
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 7) k_inter(const DevJob* __r
         if (l_uni) {
             const int i = (int)(ml & 255u);
             const PartV p = i ? p1 : p0;
-            tile_row8(sm.u.in.ref_l[i] + lrow * 32 + ((mbx * 16 + (p.mvx >> 1)) & 15) + lhalf * 8, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
+            tile_row8(sm.u.in.ref_l[i], (uint32_t)(lrow * 32 + ((mbx * 16 + (p.mvx >> 1)) & 15) + lhalf * 8), (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
         } else {
             uint32_t o[2] = {0, 0};
 #pragma unroll
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 7) k_inter(const DevJob* __r
             const int i = (int)(mc & 255u);
             const PartV p = i ? p1 : p0;
             const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-            c0 = tile_row4(sm.u.in.ref_c[i][cpl] + crow * 32 + ((mbx * 8 + (cx >> 1)) & 15) + lhalf * 4, (cx & 1) | ((cy & 1) << 1));
+            c0 = tile_row4(sm.u.in.ref_c[i][cpl], (uint32_t)(crow * 32 + ((mbx * 8 + (cx >> 1)) & 15) + lhalf * 4), (cx & 1) | ((cy & 1) << 1));
         } else {
             c0 = 0;
 #pragma unroll
@@ -366,7 +369,13 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 7) k_inter(const DevJob* __r
     if (n_coef) {
         // ---- dequantise into the compacted coefficient blocks (MD:3424-3429) ----
         const int nblk = __popc(blkmask);
-        for (int i = lane; i < nblk * 16; i += 32) reinterpret_cast<int4*>(&sm.u.coef[0][0])[i] = make_int4(0, 0, 0, 0);
+        {
+            int4* z = reinterpret_cast<int4*>(&sm.u.coef[0][0]) + lane;
+            const int nz = nblk * 16 - lane;   // <= 96: at most three rounds
+            if (nz > 0) z[0] = make_int4(0, 0, 0, 0);
+            if (nz > 32) z[32] = make_int4(0, 0, 0, 0);
+            if (nz > 64) z[64] = make_int4(0, 0, 0, 0);
+        }
         *reinterpret_cast<uint2*>(sm.tile + lrow * 16 + lhalf * 8) = make_uint2(y0, y1);
         *reinterpret_cast<uint32_t*>(sm.tile + 256 + cpl * 64 + crow * 8 + lhalf * 4) = c0;
         __syncwarp();
@@ -382,13 +391,7 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 7) k_inter(const DevJob* __r
             m8 |= is8 << blk;
         }
         m8 = __reduce_or_sync(0xffffffffu, m8);
-        // ids of the coded blocks, one nibble each, in slot order
-        uint32_t list = 0;
-        {
-            int n = 0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) if ((blkmask >> k) & 1u) { list |= (uint32_t)k << (4 * n); n++; }
-        }
+        const uint32_t list = c_blklist[blkmask];   // ids of the coded blocks, one nibble each, in slot order
         __syncwarp();
 
         // ---- inverse transforms: eight lanes per coded block (one row each), four blocks per pass ----
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32) k_inter_pipe(const DevJob* __
             if (l_uni) {
                 const int k = (int)(ml & 255u);
                 const PartV p = k ? p1 : p0;
-                tile_row8(sm.box[(set0 + k) & (PIPE_NB - 1)] + lrow * 32 + ((mbx * 16 + (p.mvx >> 1)) & 15) + lhalf * 8, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
+                tile_row8(sm.box[(set0 + k) & (PIPE_NB - 1)], (uint32_t)(lrow * 32 + ((mbx * 16 + (p.mvx >> 1)) & 15) + lhalf * 8), (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
             } else {
                 uint32_t o[2] = {0, 0};
 #pragma unroll
@@ -639,7 +642,7 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32) k_inter_pipe(const DevJob* __
                 const int k = (int)(mc & 255u);
                 const PartV p = k ? p1 : p0;
                 const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                c0 = tile_row4(sm.box[(set0 + k) & (PIPE_NB - 1)] + 640 + cpl * 384 + crow * 32 + ((mbx * 8 + (cx >> 1)) & 15) + lhalf * 4, (cx & 1) | ((cy & 1) << 1));
+                c0 = tile_row4(sm.box[(set0 + k) & (PIPE_NB - 1)] + 640 + cpl * 384, (uint32_t)(crow * 32 + ((mbx * 8 + (cx >> 1)) & 15) + lhalf * 4), (cx & 1) | ((cy & 1) << 1));
             } else {
                 c0 = 0;
 #pragma unroll
@@ -703,12 +706,7 @@ __global__ void __launch_bounds__(PIPE_WARPS * 32) k_inter_pipe(const DevJob* __
                 m8 |= is8 << blk;
             }
             m8 = __reduce_or_sync(0xffffffffu, m8);
-            uint32_t list = 0;   // ids of the coded blocks, one nibble each, in slot order
-            {
-                int n = 0;
-#pragma unroll
-                for (int k = 0; k < 6; k++) if ((blkmask >> k) & 1u) { list |= (uint32_t)k << (4 * n); n++; }
-            }
+            const uint32_t list = c_blklist[blkmask];   // ids of the coded blocks, one nibble each, in slot order
             __syncwarp();
             // inverse transforms: eight lanes per coded block (one row each), four blocks per pass
             const int g = lane >> 3, r = lane & 7, i4 = r & 3, s0 = (r >> 2) * 2;
@@ -1156,6 +1154,16 @@ __global__ void __launch_bounds__(256) k_pack_i420(const uint8_t* const* __restr
 }
 
 }  // namespace
+
+cudaError_t init_kernel_tables() {
+    uint32_t lut[64];
+    for (uint32_t m = 0; m < 64; m++) {
+        uint32_t list = 0; int n = 0;
+        for (uint32_t k = 0; k < 6; k++) if ((m >> k) & 1u) { list |= k << (4 * n); n++; }
+        lut[m] = list;
+    }
+    return cudaMemcpyToSymbol(c_blklist, lut, sizeof lut);
+}
 
 cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, bool pipelined, cudaStream_t st) {
     if (n_jobs <= 0) return cudaSuccess;

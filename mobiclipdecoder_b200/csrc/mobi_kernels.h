@@ -32,6 +32,8 @@ struct Geom {
     int W, H, S, log2S, mbw, mbh, version;
 };
 
+// Constant tables of the kernels; once per device, before the first launch.
+cudaError_t init_kernel_tables();
 // Inter macroblocks of every job: MC from the ring + dequant/IDCT/add/clip.  One warp per MB.
 // tm_l / tm_c: the ring as a rank-3 u8 tensor (Stride, 1.5*H, pictures) with boxes 32x17x1 (luma windows) and 32x9x1 (chroma windows).
 // pipelined: k_inter_pipe (one warp per run of 16 macroblocks, TMA boxes in flight ahead) instead of k_inter (one warp per macroblock).

@@ -196,6 +196,7 @@ public:
             if (!ok(cudaEventCreateWithFlags(&a.consumed, cudaEventDisableTiming), "cudaEventCreate")) return MOBI_ERR_CUDA;
         if (!ok(cudaMalloc(&ptr_d_, sizeof(void*) * (size_t)N_), "cudaMalloc(ptrs)")) return MOBI_ERR_NOMEM;
         if (!ok(cudaMallocHost(&ptr_h_, sizeof(void*) * (size_t)N_), "cudaMallocHost(ptrs)")) return MOBI_ERR_NOMEM;
+        if (!ok(init_kernel_tables(), "init_kernel_tables")) return MOBI_ERR_CUDA;
         if (!ok(cudaStreamSynchronize(stream_), "init sync")) return MOBI_ERR_CUDA;
         if (const char* e = std::getenv("MOBI_INTER_KERNEL")) pipelined_ = std::strcmp(e, "pipe") == 0;
         return make_tensor_maps();
