@@ -943,13 +943,16 @@ __device__ __forceinline__ IntraItem load_item(const IntraWork* w) {
 }
 // Everything that does not depend on neighbouring macroblocks: the op list (returned, one op per lane), the
 // coefficient records and the picture's scale table into shared memory, zeroed tiles.
+template <bool LOAD_QTAB>
 __device__ __forceinline__ uint32_t intra_prefetch(const DevJob& J, IntraSmem& sm, const IntraItem& it, int lane) {
     const int n_ops = (int)((it.info >> 2) & 127u), n_coef = (int)((it.info >> 9) & 511u);
     const uint32_t myop = lane < n_ops ? __ldg(J.ops + it.first_op + lane) : 0u;
     const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs) + it.first_coef;
     for (int i = lane; i < n_coef; i += 32) sm.cf[i] = __ldg(cf + i);
-    const uint32_t* qt = J.hdr->qtab;
-    for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
+    if (LOAD_QTAB) {
+        const uint32_t* qt = J.hdr->qtab;
+        for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
+    }
     uint4* z = reinterpret_cast<uint4*>(&sm.y[0][0]);  // y and c tiles are contiguous: 832 B = 52 x 16
     for (int i = lane; i < 52; i += 32) z[i] = make_uint4(0, 0, 0, 0);
     return myop;
@@ -966,16 +969,34 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
     // wrap onto real pixels of the next row, so the right-hand run x+16..x+23 of rows y..y+15 is staged too (otherwise
     // it is zero: not yet decoded / padding).
     const bool wrap = g.W == S && mbx == g.mbw - 1;
-    for (int i = lane; i < 45 + (wrap ? 32 : 0); i += 32) {
-        if (i < 7) *reinterpret_cast<uint32_t*>(&sm.y[0][4 * i]) = nb_luma4(J, g, yoff - S - 4 + 4 * i, m);
-        else if (i < 23) *reinterpret_cast<uint32_t*>(&sm.y[i - 6][0]) = nb_luma4(J, g, yoff + (i - 7) * S - 4, m);
+    // slot i -> (destination word in the tiles, flat source address, plane); both of a lane's loads are issued before
+    // either is stored, so the staging costs one L2 round trip
+    auto slot = [&](int i, uint32_t*& dstw, int& flat, bool& chroma) {
+        if (i < 7) { dstw = reinterpret_cast<uint32_t*>(&sm.y[0][4 * i]); flat = yoff - S - 4 + 4 * i; chroma = false; }
+        else if (i < 23) { dstw = reinterpret_cast<uint32_t*>(&sm.y[i - 6][0]); flat = yoff + (i - 7) * S - 4; chroma = false; }
         else if (i < 45) {
-            const int k = i - 23, p = k / 11, q = k % 11, base = coff + (p ? (S >> 1) : 0);
-            if (q < 3) *reinterpret_cast<uint32_t*>(&sm.c[p][0][4 * q]) = nb_chroma4(J, g, base - S - 4 + 4 * q, m);
-            else *reinterpret_cast<uint32_t*>(&sm.c[p][q - 2][0]) = nb_chroma4(J, g, base + (q - 3) * S - 4, m);
+            const int k = i - 23, p = k >= 11 ? 1 : 0, q = k - 11 * p, base = coff + (p ? (S >> 1) : 0);
+            chroma = true;
+            if (q < 3) { dstw = reinterpret_cast<uint32_t*>(&sm.c[p][0][4 * q]); flat = base - S - 4 + 4 * q; }
+            else { dstw = reinterpret_cast<uint32_t*>(&sm.c[p][q - 2][0]); flat = base + (q - 3) * S - 4; }
         } else {
             const int k = i - 45, r = k >> 1, h = k & 1;
-            *reinterpret_cast<uint32_t*>(&sm.y[1 + r][20 + 4 * h]) = nb_luma4(J, g, yoff + r * S + 16 + 4 * h, m);
+            dstw = reinterpret_cast<uint32_t*>(&sm.y[1 + r][20 + 4 * h]); flat = yoff + r * S + 16 + 4 * h; chroma = false;
+        }
+    };
+    {
+        const int n = 45 + (wrap ? 32 : 0);
+        uint32_t* d0; uint32_t* d1; int f0, f1; bool c0, c1;
+        slot(lane, d0, f0, c0);
+        const bool two = lane + 32 < n;
+        slot(two ? lane + 32 : lane, d1, f1, c1);
+        const uint32_t v0 = c0 ? nb_chroma4(J, g, f0, m) : nb_luma4(J, g, f0, m);
+        const uint32_t v1 = two ? (c1 ? nb_chroma4(J, g, f1, m) : nb_luma4(J, g, f1, m)) : 0u;
+        *d0 = v0;
+        if (two) *d1 = v1;
+        if (lane + 64 < n) {   // only in the wrap case
+            slot(lane + 64, d0, f0, c0);
+            *d0 = nb_luma4(J, g, f0, m);
         }
     }
     __syncwarp();
@@ -1023,7 +1044,7 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 8) k_intra(const DevJob* __r
         if (t >= n_work) break;
         const IntraItem it = load_item(work + t);
         const DevJob& J = jobs[it.job];
-        const uint32_t myop = intra_prefetch(J, sm, it, lane);
+        const uint32_t myop = intra_prefetch<true>(J, sm, it, lane);
         // wait for the intra neighbours whose pixels this macroblock's predictors read (host-computed mask)
         if (lane < 4 && ((it.wait >> lane) & 1u)) {
             const int nb = lane == 0 ? (int)it.m - 1 : (int)it.m - g.mbw - 2 + lane;
@@ -1065,10 +1086,14 @@ __global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __re
     const DevJob& J = jobs[pic.job];
     const IntraWork* items = work + pic.work_base;   // raster order: every macroblock of an I-picture is intra
     const int mbw = g.mbw;
+    if (warp < g.mbh) {   // the picture's scale table: once per warp, not once per macroblock
+        const uint32_t* qt = J.hdr->qtab;
+        for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
+    }
     for (int row = warp; row < g.mbh; row += KEY_WARPS) {
         for (int x = 0; x < mbw; x++) {
             const IntraItem it = load_item(items + row * mbw + x);
-            const uint32_t myop = intra_prefetch(J, sm, it, lane);
+            const uint32_t myop = intra_prefetch<false>(J, sm, it, lane);
             if (lane == 0 && row > 0 && it.wait) {
                 // neighbours by raster index (SURVEY.md 8a hazard 2): left of column 0 = last macroblock of the row above
                 // (bit 0), top-left of column 0 = last macroblock two rows up (bit 1); top-right of the last column is
@@ -1080,7 +1105,7 @@ __global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __re
                 if ((it.wait & 8u) && x + 1 < mbw) need1 = max(need1, (uint32_t)x + 2u);
                 while (s_prog[row - 1] < need1) __nanosleep(20);
                 if (need2 && row > 1) while (s_prog[row - 2] < need2) __nanosleep(20);
-                __threadfence();
+                __threadfence_block();   // the producer fenced at gpu scope before moving its counter; the pixel loads below bypass L1
             }
             __syncwarp();
             intra_reconstruct(J, g, sm, it, myop, lane);
