@@ -172,10 +172,11 @@ struct FrameParse {
             // The reference indexes Internal[] with no check: a run past the block walks into the next table.
             if (__builtin_expect(pos >= (uint32_t)n, 0)) fail(MOBI_ERR_BITSTREAM, "coefficient run past end of block");
             if (check_qt && (qt[pos] & 0xFF) >= 64u) fail(MOBI_ERR_BITSTREAM, "quantiser < 12 corrupts the scan table (MD:3909-3911)");
-            dst->level = (int16_t)level;
-            dst->pos = (uint8_t)(pos | (uint32_t)sub << 6);
-            dst->blk = (uint8_t)(tag | ((last & 1) ? 0x40 : 0));
-            dst++;
+            {   // one 32-bit store: level (s16) | pos << 16 | blk << 24 (little-endian layout of mobi_coef)
+                const uint32_t rec = ((uint32_t)level & 0xFFFFu) | (pos | (uint32_t)sub << 6) << 16 | ((uint32_t)tag | (last & 1u) << 6) << 24;
+                std::memcpy(dst, &rec, 4);
+                dst++;
+            }
             pos++;
             if (last & 1) break;
         }
@@ -356,15 +357,16 @@ struct FrameParse {
         P.mvc_[slot] = dx; P.mvc_[slot + 1] = dy;  // MD:411-412, last leaf wins
         int w = 2 << lw, h = 2 << lh;
         if ((int)ref > P.st_.decoded) fail(MOBI_ERR_REFERENCE, "P-frame references a picture that is not in the ring");
-        // CopyBlock reads (MD:418-456): luma, then both chroma planes at (dx>>1, dy>>1), half size
-        long long first = (long long)off + (long long)(dy >> 1) * S + (dx >> 1);
-        long long last = first + (long long)(h - 1 + (dy & 1)) * S + w - 1 + (dx & 1);
-        if (first < 0 || last >= (long long)S * H) fail(MOBI_ERR_RANGE, "motion vector reads outside the luma array");
-        int cdx = dx >> 1, cdy = dy >> 1;
-        long long cfirst = (long long)(off / 2) + (long long)(cdy >> 1) * S + (cdx >> 1);
-        long long clast = cfirst + S / 2 + (long long)((h >> 1) - 1 + (cdy & 1)) * S + (w >> 1) - 1 + (cdx & 1);
-        if (cfirst < 0 || clast >= (long long)S * H / 2) fail(MOBI_ERR_RANGE, "motion vector reads outside the chroma array");
+        // the packed record holds 16-bit vectors; with that established, 32-bit arithmetic below cannot overflow
         if (dx < -32768 || dx > 32767 || dy < -32768 || dy > 32767) fail(MOBI_ERR_RANGE, "motion vector outside 16 bits");
+        // CopyBlock reads (MD:418-456): luma, then both chroma planes at (dx>>1, dy>>1), half size
+        const int first = off + ((dy >> 1) << log2S) + (dx >> 1);
+        const int last = first + ((h - 1 + (dy & 1)) << log2S) + w - 1 + (dx & 1);
+        if (first < 0 || last >= (H << log2S)) fail(MOBI_ERR_RANGE, "motion vector reads outside the luma array");
+        const int cdx = dx >> 1, cdy = dy >> 1;
+        const int cfirst = (off >> 1) + ((cdy >> 1) << log2S) + (cdx >> 1);
+        const int clast = cfirst + (S >> 1) + (((h >> 1) - 1 + (cdy & 1)) << log2S) + (w >> 1) - 1 + (cdx & 1);
+        if (cfirst < 0 || clast >= ((H << log2S) >> 1)) fail(MOBI_ERR_RANGE, "motion vector reads outside the chroma array");
         int rel = off - mboff, x = rel & (S - 1), y = rel >> log2S;
         mobi_part p;
         p.xy = (uint8_t)((x >> 1) | (y >> 1) << 4);
