@@ -5,17 +5,19 @@
 // bytes, U in columns [0,Stride/2) and V in [Stride/2,Stride) of each chroma row (MD:107-108, 267-268).
 // Stride padding is zero and never written.
 //
-// k_inter : one warp per 16x16 macroblock.  Lane l owns luma row l/2, 8 pixels (one 64-bit store) and
-//           chroma plane l/16, row (l/2)%8, 4 pixels (one 32-bit store).  Motion compensation works
-//           on packed bytes (4 pixels per ALU op, truncating averages MD:418-456); the inverse
-//           transforms run one 8-point (or two 4-point) butterflies per lane with the transpose
-//           through a per-warp shared-memory tile, laid out so that the lane that finishes a row of
-//           residuals is the lane that owns those pixels.
-// k_intra : one warp per intra macroblock, executed in decode order through an atomic ticket; the
-//           neighbourhood (row above incl. top-right, column left, and the not-yet-decoded pixels to
-//           the right, which the reference reads as 0 from its freshly allocated planes MD:107) is
-//           staged in shared memory, availability decided by coordinates, never by memory contents.
-// No tensor cores: these are 8-bit fixed-point butterflies and byte shuffles, bound by HBM/LSU.
+// k_inter     : one warp per 16x16 inter macroblock.  Reference windows arrive by TMA (the ring is one rank-3 tensor) into
+//               per-warp shared memory; lane l owns luma row l/2, 8 pixels (one 64-bit store) and 4 chroma pixels;
+//               half-pel filter on packed bytes (truncating averages MD:418-456); residual: eight lanes per coded 8x8
+//               block, transpose through shared memory, saturating pack onto a prediction tile.
+// k_inter_pipe: experiment (MOBI_INTER_KERNEL=pipe): one warp per run of 16 macroblocks with the boxes of the next
+//               macroblocks in flight; measured slower than k_inter, kept for the record.
+// k_intra     : intra macroblocks inside P-pictures, one warp each, drawn by ticket from a dependency-depth-ordered list;
+//               the neighbourhood (row above incl. top-right, column left, and the not-yet-decoded pixels to the right,
+//               which the reference reads as 0 from its freshly allocated planes MD:107) is staged in shared memory,
+//               availability decided by coordinates, never by memory contents.
+// k_intra_key : I-pictures, one CTA per picture, one warp per macroblock row, progress counters in shared memory.
+// k_bgra / k_pack_i420: output conversions.
+// No tensor cores: these are 8-bit fixed-point butterflies and byte shuffles.
 #include "mobi_kernels.h"
 
 namespace mobi {

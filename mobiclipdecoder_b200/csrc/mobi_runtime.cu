@@ -59,7 +59,6 @@ public:
         done_.wait(l, [this] { return active_ == 0; });
         fn_ = nullptr;
     }
-    int size() const { return (int)th_.size(); }
 private:
     void work() {
         for (;;) {
@@ -736,9 +735,9 @@ private:
         if (L.n_work_p) {
             uint32_t warps = 0;
             if (timing_) tick(1, stream_);
-            if (!ok(launch_intra(jobs, work, L.n_work_p, ticket_, ticket_base_[0], stamp_, g_, (uint32_t)sm_count_ * 32u, stream_, &warps), "k_intra(P)")) return MOBI_ERR_CUDA;
+            if (!ok(launch_intra(jobs, work, L.n_work_p, ticket_, ticket_base_, stamp_, g_, (uint32_t)sm_count_ * 32u, stream_, &warps), "k_intra(P)")) return MOBI_ERR_CUDA;
             if (timing_) tick(1, stream_);
-            ticket_base_[0] += L.n_work_p + warps;
+            ticket_base_ += L.n_work_p + warps;
             stats_.launches++;
         }
         if (n_key && !ok(cudaStreamWaitEvent(stream_, join_, 0), "cudaStreamWaitEvent")) return MOBI_ERR_CUDA;
@@ -824,7 +823,7 @@ private:
     uint8_t* ring_ = nullptr;
     uint32_t* flags_ = nullptr;
     uint32_t* ticket_ = nullptr;
-    uint32_t ticket_base_[2] = {0, 0}, stamp_ = 0, key_resident_ = 0;
+    uint32_t ticket_base_ = 0, stamp_ = 0, key_resident_ = 0;   // ticket_[0]: work tickets of k_intra; ticket_[32]: resident I-picture CTAs
     CUtensorMap tm_l_, tm_c_;
     bool pipelined_ = false;  // MOBI_INTER_KERNEL=pipe selects k_inter_pipe (one warp per run of 16 macroblocks; measured slower)
     cudaStream_t side_ = nullptr, copy_ = nullptr;

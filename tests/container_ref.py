@@ -58,9 +58,8 @@ def write_moc5(frames, width, height, fps_x128=30 * 128, header_len=0xE0):
     for p, _ in frames:
         block = struct.pack('<I', 0) + p      # what lies between the size word and the next block: 4 bytes + payload
         bs = len(block)
+        assert bs % 2 == 0   # the reader steps by size & ~1 (Form1.cs:317): payloads are whole 16-bit words
         body += struct.pack('<I', bs) + block
-        if bs & 1:
-            body = body[:-1] if False else body   # size & ~1 drops an odd byte: keep payloads even (the generator's are)
         while (len(hdr) + len(body)) % 4:
             body += b'\\0'
     return bytes(hdr) + bytes(body)
