@@ -190,3 +190,34 @@ def test_pipelined_submit_fetch_matches_oracle():
         with pytest.raises(Exception):
             b.fetch()   # nothing outstanding
         b.close()
+
+
+def test_batch_stream_failure_is_isolated():
+    """A stream whose frame cannot be parsed sits the step out (status < 0, its picture unchanged) ; the other
+    streams advance bit-exactly.  (The failed stream itself is out of contract from then on: the
+    reference leaves a half-written picture in its ring, MD:325, this library leaves the ring untouched.)"""
+    name, n_streams, n_frames = 'moflex_400x240', 4, 9
+    w, h, ver, _ = CONFIGS[name]
+    streams = [frames(name, 500 + s, n_frames, gop=4) for s in range(n_streams)]
+    oracles = [Oracle(w, h, ver) for _ in range(n_streams)]
+    b = MobiBatch(w, h, ver, n_streams, n_threads=2)
+    before = None
+    for f in range(n_frames):
+        batch_in = [streams[s][f][0] for s in range(n_streams)]
+        if f == 2:
+            batch_in[1] = batch_in[1][:1]           # not even one 16-bit word: ReadU16LE throws in the reference (IO:39)
+            before = b.read_yuv()[1].copy()
+        offs, status = b.decode(batch_in)
+        assert status[0] == status[2] == status[3] == 0
+        if f < 2:
+            assert status[1] == 0
+        if f == 2:
+            assert status[1] < 0
+        # afterwards stream 1 may fail again (its ring is one picture short of what the stream references) or succeed
+        got = b.read_yuv()
+        if f == 2:
+            assert np.array_equal(got[1], before)   # newest picture of the failed stream is still the previous one
+        for s in (0, 2, 3):
+            assert oracles[s].decode(streams[s][f][0], 0, False)[0]
+            assert np.array_equal(got[s], oracles[s].i420()), 'stream %d frame %d' % (s, f)
+    b.close()
