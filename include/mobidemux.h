@@ -4,7 +4,7 @@
  *
  *   Mods (Nintendo DS)   LibMobiclip/Containers/Mods/ModsDemuxer.cs
  *   MOC5 (Wii)           framing parsed ad hoc in MobiclipDecoder/Form1.cs:282-320 (the CLI refuses MOC5, Program.cs:360-366)
- * Moflex (3DS) packet / end-point reassembly (MoLiveDemux.cs) is not built yet.
+ *   Moflex (3DS)         LibMobiclip/Containers/Moflex/MoLiveDemux.cs (packets, stream table, end-point reassembly)
  */
 #ifndef MOBIDEMUX_H
 #define MOBIDEMUX_H
@@ -48,6 +48,35 @@ int mobi_moc5_open(const uint8_t* data, size_t len, mobi_moc5_info* info);
  * together with the whole file as Data.  Returns 1 per frame, 0 when cursor >= len (Form1.cs:294), <0 on a block header
  * outside the file. */
 int mobi_moc5_next(const uint8_t* data, size_t len, uint32_t* cursor, uint32_t* decode_offset, uint32_t* block_size);
+
+/* ---- Moflex (3DS): MoLiveDemux (MoLiveDemux.cs:11-416) -------------------------------------------------------------
+ * Packets start with an optional synchro header ("L2", checksum, 64-bit timestamp, packet size; :375-414) followed by
+ * synchro chunks describing the streams (:168-215), then a data block flag byte (:217-268) and end-points: bit-packed
+ * headers (stream index, end-of-frame marker, 13-bit size; :270-373) each followed by a slice of a stream's current
+ * frame.  A frame is complete at an end-point flagged EndFrame; two zero bytes are appended (:353) and the
+ * OnCompleteFrameReceived event fires -- here: the frame is queued for mobi_moflex_next_frame. */
+typedef struct mobi_moflex mobi_moflex_t;
+
+typedef struct mobi_moflex_stream {   /* the MoLiveStream* chunk of the frame's stream */
+    int32_t stream_index;
+    uint32_t chunk_id;                /* 1 MoLiveStreamVideo, 2 MoLiveStreamAudio, 3 MoLiveStreamVideoWithLayout, 4 MoLiveStreamTimeline */
+    uint32_t codec_id;
+    uint32_t fps_rate, fps_scale, width, height, pel_ratio_rate, pel_ratio_scale;  /* video (MoLiveStreamVideo.cs:33-49) */
+    uint32_t image_layout, image_rotation;                                        /* chunk 3 (MoLiveStreamVideoWithLayout.cs) */
+    uint32_t frequency, channels;                                                 /* audio (MoLiveStreamAudio.cs) */
+    uint32_t associated_stream_index;                                             /* timeline */
+} mobi_moflex_stream;
+
+int mobi_moflex_open(const uint8_t* data, size_t len, mobi_moflex_t** out);
+void mobi_moflex_close(mobi_moflex_t* m);
+/* MoLiveDemux.ReadPacket() (:67-164).  Returns the reference's status code: 0 packet consumed (or resynchronised), 1 fewer
+ * than 14 bytes left, 0x80 no synchro pattern, 73 short / inconsistent packet (the CLI's end condition, Program.cs:162-166),
+ * 0x43-0x50 framing errors (the demuxer desynchronises as the reference does).  Where the reference would throw
+ * (index outside the 4 KiB packet buffer, duplicate stream index) 0x43 / 0x45 is returned instead. */
+uint32_t mobi_moflex_read_packet(mobi_moflex_t* m);
+/* Oldest completed frame not yet handed out.  Returns 1 and fills the outputs (valid until the next call on this handle),
+ * 0 when none is queued. */
+int mobi_moflex_next_frame(mobi_moflex_t* m, mobi_moflex_stream* stream, const uint8_t** data, uint32_t* len);
 
 #ifdef __cplusplus
 }

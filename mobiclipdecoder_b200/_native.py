@@ -86,8 +86,18 @@ class Moc5Info(C.Structure):
     _fields_ = [('width', C.c_uint32), ('height', C.c_uint32), ('fps_x128', C.c_uint32), ('first_block', C.c_uint32)]
 
 
+class MoflexStream(C.Structure):
+    _fields_ = [('stream_index', C.c_int32)] + [(n, C.c_uint32) for n in (
+        'chunk_id', 'codec_id', 'fps_rate', 'fps_scale', 'width', 'height', 'pel_ratio_rate', 'pel_ratio_scale', 'image_layout',
+        'image_rotation', 'frequency', 'channels', 'associated_stream_index')]
+
+
 # every symbol include/mobidemux.h declares (same library)
 MOBIDEMUX_EXPORTS = {
+    'mobi_moflex_open': (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    'mobi_moflex_close': (None, [C.c_void_p]),
+    'mobi_moflex_read_packet': (C.c_uint32, [C.c_void_p]),
+    'mobi_moflex_next_frame': (C.c_int, [C.c_void_p, C.POINTER(MoflexStream), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
     'mobi_mods_open': (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     'mobi_mods_close': (None, [C.c_void_p]),
     'mobi_mods_get_header': (C.c_int, [C.c_void_p, C.POINTER(ModsHeader)]),

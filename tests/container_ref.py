@@ -77,3 +77,59 @@ def read_moc5_reference(data):
         while offs % 4:
             offs += 1
     return (w, h, fps), out
+
+
+# ---- Moflex writer: MoflexMuxer.cs:21-95 + MoflexSimpleVideoMuxer.cs:13-70 restated (the reference's own writer) ----
+def _variable_byte(v):
+    assert v < (1 << 28)
+    if v < 0x80:
+        return bytes([v])
+    if v < 0x2000:
+        return bytes([(v >> 7) | 0x80, v & 0x7F])
+    if v < 0x200000:
+        return bytes([(v >> 14) | 0x80, ((v >> 7) & 0x7F) | 0x80, v & 0x7F])
+    return bytes([((v >> 21) | 0x80) & 0xFF, ((v >> 14) | 0x80) & 0xFF, ((v >> 7) & 0x7F) | 0x80, v & 0x7F])
+
+
+def _synchro_header(ts=1, packet_size_field=0x1000):
+    hi = (ts >> 32) & 0xFFFFFFFF
+    v19 = hi & 0x7FFFFFFF if ((hi - 1) & 0xFFFFFFFF) >= 0x80000000 else hi
+    crc = ((ts >> 16) & 0xFFFF) ^ (v19 >> 16) ^ 0xAAAA ^ (v19 & 0xFFFF) ^ (ts & 0xFFFF)
+    return b'L2' + struct.pack('>HQH', crc & 0xFFFF, ts, packet_size_field)
+
+
+def _video_chunk(stream_index, codec_id, fps_rate, fps_scale, w, h):
+    body = struct.pack('>BBHHHHBB', stream_index, codec_id, fps_rate, fps_scale, w, h, 1, 1)
+    return _variable_byte(1) + _variable_byte(12) + body
+
+
+def _ep(ep, data, end_frame):
+    """WriteEp (MoflexMuxer.cs:52-94); like the reference's writer this is only right for Ep 0 and 1."""
+    if data is None:
+        return b'\0'
+    nrbits = 1 if ep == 0 else ep.bit_length()
+    bits = '0' * (nrbits - 1) + '1' + format(ep, '0%db' % nrbits) + ('1' if end_frame else '0')
+    if end_frame:
+        bits += '1' + '0' + '0' + '1' + '0' * 28     # frame type 1 bit = 1; sign 0; ts length marker; 28-bit timestamp 0
+    bits += format(len(data) - 1, '013b')
+    nbytes = (len(bits) + 4) // 8
+    bits = bits.ljust(nbytes * 8, '0')
+    return int(bits, 2).to_bytes(nbytes, 'big') + data
+
+
+def write_moflex(frames, width, height, fps_rate=24, fps_scale=1, max_ep=0x1000 - 0x80):
+    """frames: list of payload bytes (without the two pad bytes the demuxer appends)."""
+    out = bytearray(_synchro_header() + _video_chunk(0, 0, fps_rate, fps_scale, width, height) + _variable_byte(0) + _variable_byte(0))
+    for data in frames:
+        pos, left = 0, len(data)
+        if left <= max_ep:
+            out += b'\x01' + _ep(0, data, True) + _ep(0, None, False)
+            continue
+        while left >= max_ep:
+            out += b'\x01' + _ep(0, data[pos:pos + max_ep], left == max_ep) + _ep(0, None, False)
+            pos += max_ep
+            left -= max_ep
+        if left > 0:
+            out += b'\x01' + _ep(0, data[pos:pos + left], True) + _ep(0, None, False)
+    out += bytes(0x1000)    # FinalizeMoflex
+    return bytes(out)
