@@ -41,7 +41,7 @@ WORKLOAD = 'moflex_400x240'
 BASE_SEED = 1000
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
 # (profiles/): filled in after each capture, None until then.
-NCU_TRAFFIC = {'k_inter': 5.54e8}   # profiles/r01h_prof_summary.csv: (392.6 + 142.6 MB, 430.2 + 141.8 MB) / 2 per launch
+NCU_TRAFFIC = {'k_inter': 5.53e8}   # profiles/r01i_prof_summary.csv: (392.0 + 142.5 MB, 429.8 + 141.7 MB) / 2 per launch
 
 
 def load_peaks():
