@@ -52,7 +52,16 @@ struct Parser::Bits {
         win |= w << ((16 - nb) & 31);
     }
     void drop(int n) { win <<= (n & 31); nb -= n; }
-    void chk() { if (nb < 0) fill(); }
+    // FillBits when the counter is negative (MD:2988-2996).  Whether it is negative is data-dependent and poorly
+    // predicted, so while a whole word is available the refill is done arithmetically; the last word takes fill().
+    void chk() {
+        if (__builtin_expect(off + 1 < len, 1)) {
+            const uint32_t m = (uint32_t)(nb >> 31);
+            const uint32_t w = (uint32_t)d[off] | (uint32_t)d[off + 1] << 8;
+            nb += (int)(16u & m); off += (int)(2u & m);
+            win |= (w << ((16 - nb) & 31)) & m;
+        } else if (nb < 0) fill();
+    }
     uint32_t take(int n) { uint32_t v = win >> (32 - n); drop(n); chk(); return v; }
     uint32_t gamma() {
         int z = win ? __builtin_clz(win) : 32;
@@ -63,11 +72,11 @@ struct Parser::Bits {
         v += (uint32_t)(1u << (z & 31));
         win <<= (z & 31);
         nb -= z << 1;
-        if (--nb < 0) fill();
+        --nb; chk();
         return v;
     }
     uint32_t uvar() { return gamma() - 1; }
-    int svar() { int v = (int)gamma(); if (v & 1) v = 1 - v; return v >> 1; }
+    int svar() { const int v = (int)gamma(), n = -(v & 1); return ((v ^ n) - n + (v & 1)) >> 1; }   // odd v: (1 - v) >> 1, even v: v >> 1, branch-free
 };
 
 struct FrameParse {
@@ -120,8 +129,17 @@ struct FrameParse {
         int nb = b.nb, off = b.off;
         mobi_coef* dst = &out.coefs.v[out.coefs.n];
         const uint8_t tag = (uint8_t)(blk | (n == 64 ? 0x80 : 0));
-#define MOBI_CHK() do { if (nb < 0 && off < len) { if (off + 1 >= len) fail(MOBI_ERR_BITSTREAM, "read past end of frame data"); \
-                                                    const uint32_t w_ = (uint32_t)data[off] | (uint32_t)data[off + 1] << 8; off += 2; nb += 16; win |= w_ << ((16 - nb) & 31); } } while (0)
+        // Refill (MD:2988-2996) without a data-dependent branch: whether the counter went negative is close to a coin flip
+        // per coefficient, so the common case (a whole word is still available) does it arithmetically; the tail of the
+        // buffer takes the literal path.
+#define MOBI_CHK() do { \
+            if (__builtin_expect(off + 1 < len, 1)) { \
+                const uint32_t m_ = (uint32_t)(nb >> 31);                                   /* all ones iff nb < 0 */ \
+                const uint32_t w_ = (uint32_t)data[off] | (uint32_t)data[off + 1] << 8; \
+                nb += (int)(16u & m_); off += (int)(2u & m_); \
+                win |= (w_ << ((16 - nb) & 31)) & m_; \
+            } else if (nb < 0 && off < len) fail(MOBI_ERR_BITSTREAM, "read past end of frame data"); \
+        } while (0)
         uint32_t pos = 0;
         for (;;) {
             int run, level, nbits;
@@ -404,14 +422,14 @@ struct FrameParse {
         if ((b.win >> 31) & 1) { b.win += b.win; b.nb--; coefs(64, blk, 0, mask); }
         else {
             uint32_t cbp4 = tab(MOBI_CBP4_INTER, 16, b.uvar());
-            for (int k = 0; k < 4; k++) if ((cbp4 >> k) & 1) coefs(16, blk, (uint8_t)k, mask);
+            for (uint32_t m = cbp4 & 15u; m; m &= m - 1) coefs(16, blk, (uint8_t)__builtin_ctz(m), mask);
         }
     }
     void inter_mb(int mboff, int slot) {
         uint32_t first_part = (uint32_t)out.parts.size(), first_coef = (uint32_t)out.coefs.size(), mask = 0;
         if (!pblock(3, 3, mboff, mboff, slot)) return;
         uint32_t cbp6 = tab(MOBI_CBP6_INTER, 64, b.uvar());  // loc_1161A0 MD:1818
-        for (int k = 0; k < 6; k++) if ((cbp6 >> k) & 1) blk8_inter((uint8_t)k, mask);
+        for (uint32_t m = cbp6 & 63u; m; m &= m - 1) blk8_inter((uint8_t)__builtin_ctz(m), mask);   // set bits only, ascending: no coin-flip branch per block
         mobi_mb mb;
         uint32_t np = (uint32_t)out.parts.size() - first_part, nco = (uint32_t)out.coefs.size() - first_coef;
         mb.info = 0u | np << 2 | nco << 9 | mask << 18;
@@ -427,12 +445,10 @@ struct FrameParse {
         out.hdr.n_inter_coefs += nco;
     }
 
-    static int med3(int a, int c, int e) {  // MD:171-188
-        int t;
-        if (a > c) { t = a; a = c; c = t; }
-        if (c > e) { t = c; c = e; e = t; }
-        if (a > c) { t = a; a = c; c = t; }
-        return c;
+    static int med3(int a, int c, int e) {  // the sorting network of MD:171-188 leaves the median in the middle; min/max form: no branches
+        const int lo = a < c ? a : c, hi = a < c ? c : a;
+        const int m = hi < e ? hi : e;
+        return lo > m ? lo : m;
     }
 
     void run(const uint8_t* data, int len, int start) {
