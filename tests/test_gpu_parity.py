@@ -221,3 +221,43 @@ def test_batch_stream_failure_is_isolated():
             assert oracles[s].decode(streams[s][f][0], 0, False)[0]
             assert np.array_equal(got[s], oracles[s].i420()), 'stream %d frame %d' % (s, f)
     b.close()
+
+
+def test_config3_full_length_stream():
+    """BASELINE config 3 at full length: one 400x240 Moflex3DS stream, 1024 frames, I-picture every 90; every picture's planes
+    against the oracle (long P-chains: an error anywhere propagates, so this is also the drift check)."""
+    name, n_frames = 'moflex_400x240', 1024
+    w, h, ver, _ = CONFIGS[name]
+    s = make_stream(name, 3)
+    dec, ora = MobiclipDecoder(w, h, ver), Oracle(w, h, ver)
+    for i in range(n_frames):
+        data, key = s.next_frame()
+        assert key == (i % 90 == 0)
+        dec.Data, dec.Offset = data, 0
+        assert dec.DecodeFrame(want_bitmap=False) is not None, 'frame %d: %s' % (i, dec.last_error())
+        ok, off, _ = ora.decode(data, 0, False)
+        assert ok and off == dec.Offset
+        if i % 8 == 0 or key or i == n_frames - 1:     # planes every 8th picture, every key picture and the last one
+            assert np.array_equal(dec.Y[0], ora.y) and np.array_equal(dec.UV[0], ora.uv), 'frame %d' % i
+    dec.close()
+
+
+def test_config5_eight_streams_lockstep():
+    """BASELINE config 5 per GPU share: independent 400x240 streams with seeds 1..8 advancing in lock step."""
+    name, n_streams, n_frames = 'moflex_400x240', 8, 100
+    w, h, ver, _ = CONFIGS[name]
+    gens = [make_stream(name, 1 + s) for s in range(n_streams)]
+    oracles = [Oracle(w, h, ver) for _ in range(n_streams)]
+    b = MobiBatch(w, h, ver, n_streams, n_threads=4)
+    for f in range(n_frames):
+        batch_in = [g.next_frame()[0] for g in gens]
+        offs, status = b.decode(batch_in)
+        assert all(st == 0 for st in status)
+        for s in range(n_streams):
+            ok, off, _ = oracles[s].decode(batch_in[s], 0, False)
+            assert ok and off == offs[s]
+        if f % 10 == 9 or f == 90:
+            got = b.read_yuv()
+            for s in range(n_streams):
+                assert np.array_equal(got[s], oracles[s].i420()), 'stream %d frame %d' % (s, f)
+    b.close()
