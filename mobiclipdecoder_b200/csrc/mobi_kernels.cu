@@ -1078,7 +1078,7 @@ struct KeyPic { uint32_t job, work_base; };
 __global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __restrict__ jobs, const IntraWork* __restrict__ work,
                                                               const KeyPic* __restrict__ pics, Geom g, uint32_t* resident) {
     __shared__ __align__(16) IntraSmem s_all[KEY_WARPS];
-    __shared__ volatile uint32_t s_prog[64];   // macroblocks finished per macroblock row (H <= 1024)
+    __shared__ uint32_t s_prog[64];   // macroblocks finished per macroblock row (H <= 1024); accessed with atomics only
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) atomicAdd(resident, 1u);   // this CTA holds its SM resources now (see k_gate)
     if (threadIdx.x < 64) s_prog[threadIdx.x] = 0;
@@ -1105,8 +1105,8 @@ __global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __re
                 if (it.wait & 2u) { if (x == 0) need2 = (uint32_t)mbw; else need1 = max(need1, (uint32_t)x); }
                 if (it.wait & 4u) need1 = max(need1, (uint32_t)x + 1u);
                 if ((it.wait & 8u) && x + 1 < mbw) need1 = max(need1, (uint32_t)x + 2u);
-                while (s_prog[row - 1] < need1) __nanosleep(20);
-                if (need2 && row > 1) while (s_prog[row - 2] < need2) __nanosleep(20);
+                while (atomicAdd(&s_prog[row - 1], 0u) < need1) __nanosleep(20);
+                if (need2 && row > 1) while (atomicAdd(&s_prog[row - 2], 0u) < need2) __nanosleep(20);
                 __threadfence_block();   // the producer fenced at gpu scope before moving its counter; the pixel loads below bypass L1
             }
             __syncwarp();
@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __re
             __syncwarp();
             if (lane == 0) {
                 __threadfence();            // the row's pixels are in L2 before the counter moves
-                s_prog[row] = (uint32_t)x + 1u;
+                atomicExch(&s_prog[row], (uint32_t)x + 1u);
             }
         }
     }
