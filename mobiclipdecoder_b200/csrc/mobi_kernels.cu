@@ -9,8 +9,6 @@
 //               per-warp shared memory; lane l owns luma row l/2, 8 pixels (one 64-bit store) and 4 chroma pixels;
 //               half-pel filter on packed bytes (truncating averages MD:418-456); residual: eight lanes per coded 8x8
 //               block, transpose through shared memory, saturating pack onto a prediction tile.
-// k_inter_pipe: experiment (MOBI_INTER_KERNEL=pipe): one warp per run of 16 macroblocks with the boxes of the next
-//               macroblocks in flight; measured slower than k_inter, kept for the record.
 // k_intra     : intra macroblocks inside P-pictures, one warp each, drawn by ticket from a dependency-depth-ordered list;
 //               the neighbourhood (row above incl. top-right, column left, and the not-yet-decoded pixels to the right,
 //               which the reference reads as 0 from its freshly allocated planes MD:107) is staged in shared memory,
@@ -447,319 +445,6 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 7) k_inter(const DevJob* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// inter macroblocks, pipelined: one warp walks a run of PIPE_RUN consecutive macroblocks of a picture.  Descriptors,
-// leaf records and the scale table of the run are fetched once; the TMA boxes of up to PIPE_NB macroblocks ahead are in
-// flight while the current macroblock is filtered, transformed and stored, so no warp ever sits out a memory round
-// trip, and the per-macroblock prologue of the one-warp-per-macroblock kernel is paid once per run.
-// ------------------------------------------------------------------------------------------------
-constexpr int PIPE_RUN = 16, PIPE_NB = 4, PIPE_WARPS = 4, PIPE_PARTS = 128;
-constexpr int BOX_STRIDE = 640 + 2 * 384;   // luma box (544 -> 640) + U box + V box (288 -> 384 each), 128-byte aligned
-struct PipeSmem {
-    uint8_t box[PIPE_NB][BOX_STRIDE];   // ring of box sets (luma 640 + U 384 + V 384)
-    int32_t coef[6][64];                // coefficient blocks of the current macroblock's coded 8x8 blocks (compacted)
-    uint8_t tile[384];                  // its prediction + residual
-    uint2 parts[PIPE_PARTS];            // leaf records of the run (those not carried inline); overflow is read from global
-    uint32_t qtab[80];
-    uint8_t map[64];
-    uint64_t bar[PIPE_NB];
-    uint8_t pad[96];
-};
-static_assert(sizeof(PipeSmem) % 128 == 0, "per-warp shared memory must keep TMA destinations 128-byte aligned");
-
-template <int LOG2S>
-__global__ void __launch_bounds__(PIPE_WARPS * 32) k_inter_pipe(const DevJob* __restrict__ jobs, int mbw, uint32_t mbw_magic, int H,
-                                                                const __grid_constant__ CUtensorMap tm_l, const __grid_constant__ CUtensorMap tm_c) {
-    __shared__ __align__(128) PipeSmem s_all[PIPE_WARPS];
-    constexpr int S = 1 << LOG2S;
-    const DevJob& J = jobs[blockIdx.y];
-    const uint32_t n_mb = J.n_mb;
-    if (J.n_intra == n_mb) return;  // I-picture: nothing for this kernel
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t mb0 = (blockIdx.x * PIPE_WARPS + warp) * PIPE_RUN;
-    if (mb0 >= n_mb) return;
-    const int count = (int)min((uint32_t)PIPE_RUN, n_mb - mb0);
-    PipeSmem& sm = s_all[warp];
-
-    // ---- once per run ----
-    uint4 d = make_uint4(3u, 0u, 0u, 0u);   // lane l keeps the descriptor of macroblock mb0 + l; kind 3 = not ours
-    if (lane < count) d = __ldg(reinterpret_cast<const uint4*>(J.mbs + mb0 + lane));
-    const bool mine_inter = (d.x & 3u) == 0u;
-    const uint32_t inter_mask = __ballot_sync(0xffffffffu, mine_inter);
-    if (!inter_mask) return;
-    const int my_np = mine_inter ? (int)((d.x >> 2) & 127u) : 0, my_nc = mine_inter ? (int)((d.x >> 9) & 511u) : 0;
-    const bool my_inline = mine_inter && my_np == 1 && (d.x & (1u << 28));
-    {
-        const uint32_t* qt = J.hdr->qtab;
-        for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
-    }
-    const int kfirst = __ffs(inter_mask) - 1, klast = 31 - __clz(inter_mask);
-    const uint32_t pt_lo = __shfl_sync(0xffffffffu, d.y, kfirst);   // leaves of the run's inter macroblocks are contiguous
-    {
-        const uint32_t pt_hi = __shfl_sync(0xffffffffu, d.y, klast) + __shfl_sync(0xffffffffu, (uint32_t)my_np, klast);
-        if (__ballot_sync(0xffffffffu, mine_inter && !my_inline)) {
-            const uint32_t n = min(pt_hi - pt_lo, (uint32_t)PIPE_PARTS);
-            for (uint32_t i = lane; i < n; i += 32) sm.parts[i] = __ldg(reinterpret_cast<const uint2*>(J.parts + pt_lo + i));
-        }
-    }
-    if (lane < PIPE_NB) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.bar[lane])) : "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // init visible to the async (TMA) proxy; CTA scope: no L1 invalidate
-    __syncwarp();
-    auto leaf_at = [&](uint32_t idx) {   // idx relative to pt_lo
-        const uint2 w = idx < (uint32_t)PIPE_PARTS ? sm.parts[idx] : __ldg(reinterpret_cast<const uint2*>(J.parts + pt_lo + idx));
-        return part_of(w.x, w.y);
-    };
-    const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs);
-    uint32_t c_next = 0;   // first 32 coefficient records of the next inter macroblock
-    {
-        const uint32_t z = __shfl_sync(0xffffffffu, d.z, kfirst), n = __shfl_sync(0xffffffffu, (uint32_t)my_nc, kfirst);
-        if ((uint32_t)lane < n) c_next = __ldg(cf + z + lane);
-    }
-    const size_t ysz = (size_t)S * H;
-    const int lrow = lane >> 1, lhalf = lane & 1;
-    const int cpl = lane >> 4, crow = (lane >> 1) & 7;
-
-    int head = 0, boxhead = 0, freesets = PIPE_NB;
-    uint32_t phases = 0;
-    uint32_t my_state = 0;   // lane l: bit 0 boxes issued for macroblock l, bits 1-2 first box set, bit 3 barrier parity
-
-    for (int i = 0; i < count; i++) {
-        // ---- producer: issue the boxes of the macroblocks ahead ----
-        while (head < count && head < i + PIPE_NB) {
-            if (!((inter_mask >> head) & 1u)) { head++; continue; }
-            const uint32_t dx = __shfl_sync(0xffffffffu, d.x, head), dy = __shfl_sync(0xffffffffu, d.y, head), dw = __shfl_sync(0xffffffffu, d.w, head);
-            const int np = (int)((dx >> 2) & 127u);
-            const uint32_t mbh = mb0 + (uint32_t)head;
-            const int mby = (int)__umulhi(mbh, mbw_magic), mbx = (int)mbh - mby * mbw;
-            PartV p0, p1;
-            p1.mvx = p1.mvy = 0; p1.ref = 1;
-            if (np == 1 && (dx & (1u << 28))) { p0.mvx = ((int)(dw << 18)) >> 18; p0.mvy = ((int)(dw << 4)) >> 18; p0.ref = (int)(dw >> 28); }
-            else { p0 = leaf_at(dy - pt_lo); if (np > 1) p1 = leaf_at(dy - pt_lo + 1); }
-            bool elig = np <= 2;
-            {
-                const int x0 = mbx * 16 + (p0.mvx >> 1), cx0 = mbx * 8 + (p0.mvx >> 2);
-                elig = elig && x0 >= 0 && x0 + 17 <= S && cx0 >= 0 && cx0 + 9 <= (S >> 1);
-                const int x1 = mbx * 16 + (p1.mvx >> 1), cx1 = mbx * 8 + (p1.mvx >> 2);
-                if (np == 2) elig = elig && x1 >= 0 && x1 + 17 <= S && cx1 >= 0 && cx1 + 9 <= (S >> 1);
-            }
-            if (elig && np > freesets) break;   // the consumer below frees box sets; the oldest macroblock always fits
-            uint32_t st = 0;
-            if (elig) {
-                const int b = head & (PIPE_NB - 1);
-                st = 1u | (uint32_t)boxhead << 1 | ((phases >> b) & 1u) << 3;
-                phases ^= 1u << b;
-                if (lane == 0) {
-                    const uint32_t bar = smem_u32(&sm.bar[b]);
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)np * (TMA_BYTES_L + 2 * TMA_BYTES_C)) : "memory");
-                    for (int k = 0; k < np; k++) {
-                        const PartV p = k ? p1 : p0;
-                        const int pic = (int)J.ref_pic[p.ref - 1];
-                        const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                        const int xl = mbx * 16 + (p.mvx >> 1), xc = mbx * 8 + (cx >> 1);
-                        const uint32_t dst = smem_u32(sm.box[(boxhead + k) & (PIPE_NB - 1)]);
-                        tma_load_3d(dst, &tm_l, xl & ~15, mby * 16 + (p.mvy >> 1), pic, bar);
-                        tma_load_3d(dst + 640, &tm_c, xc & ~15, H + mby * 8 + (cy >> 1), pic, bar);
-                        tma_load_3d(dst + 1024, &tm_c, (S >> 1) + (xc & ~15), H + mby * 8 + (cy >> 1), pic, bar);
-                    }
-                }
-                boxhead = (boxhead + np) & (PIPE_NB - 1);
-                freesets -= np;
-            }
-            if (lane == head) my_state = st;
-            head++;
-        }
-        if (!((inter_mask >> i) & 1u)) continue;
-
-        // ---- consumer: macroblock i ----
-        const uint32_t dx = __shfl_sync(0xffffffffu, d.x, i), dy = __shfl_sync(0xffffffffu, d.y, i), dz = __shfl_sync(0xffffffffu, d.z, i),
-                       dw = __shfl_sync(0xffffffffu, d.w, i);
-        const uint32_t st = __shfl_sync(0xffffffffu, my_state, i);
-        const int n_parts = (int)((dx >> 2) & 127u), n_coef = (int)((dx >> 9) & 511u);
-        const uint32_t blkmask = (dx >> 18) & 63u;
-        const uint32_t pbase = dy - pt_lo;
-        const uint32_t c_first = c_next;
-        {   // prefetch the next inter macroblock's first coefficient records
-            const uint32_t later = inter_mask & ~((2u << i) - 1u);
-            c_next = 0;
-            if (later) {
-                const int nx = __ffs(later) - 1;
-                const uint32_t z = __shfl_sync(0xffffffffu, d.z, nx), n = __shfl_sync(0xffffffffu, (uint32_t)my_nc, nx);
-                if ((uint32_t)lane < n) c_next = __ldg(cf + z + lane);
-            }
-        }
-        const uint32_t mbi = mb0 + (uint32_t)i;
-        const int mby = (int)__umulhi(mbi, mbw_magic), mbx = (int)mbi - mby * mbw;
-        const int yoff = ((mby * 16) << LOG2S) + mbx * 16, coff = yoff >> 1;
-        const int ypix = yoff + (lrow << LOG2S) + lhalf * 8;                           // this lane's luma pixels
-        const int cpix = coff + (cpl ? (S >> 1) : 0) + (crow << LOG2S) + lhalf * 4;    // this lane's chroma pixels
-        PartV p0, p1;
-        p1.mvx = p1.mvy = 0; p1.ref = 1;
-        if (n_parts == 1 && (dx & (1u << 28))) { p0.mvx = ((int)(dw << 18)) >> 18; p0.mvy = ((int)(dw << 4)) >> 18; p0.ref = (int)(dw >> 28); }
-        else { p0 = leaf_at(pbase); if (n_parts > 1) p1 = leaf_at(pbase + 1); }
-        // which leaf covers each of this lane's 2x2 cells (split macroblocks)
-        uint32_t ml = 0, mc = 0;
-        if (n_parts > 1) {
-            const int cy2 = lane >> 2, cx2 = (lane & 3) * 2;
-            uint32_t i0 = 0, i1 = 0;
-            for (int k = 0; k < n_parts; k++) {
-                const uint32_t idx = pbase + (uint32_t)k;
-                const uint32_t w = idx < (uint32_t)PIPE_PARTS ? sm.parts[idx].x : __ldg(reinterpret_cast<const uint32_t*>(J.parts + pt_lo + idx));
-                const int x2 = w & 15, y2 = (w >> 4) & 15, cw = 1 << ((w >> 8) & 3), ch = 1 << ((w >> 10) & 3);
-                const bool rowin = (unsigned)(cy2 - y2) < (unsigned)ch;
-                if (rowin && (unsigned)(cx2 - x2) < (unsigned)cw) i0 = (uint32_t)k;
-                if (rowin && (unsigned)(cx2 + 1 - x2) < (unsigned)cw) i1 = (uint32_t)k;
-            }
-            __syncwarp();
-            reinterpret_cast<uint16_t*>(sm.map)[lane] = (uint16_t)(i0 | i1 << 8);
-            __syncwarp();
-            ml = *reinterpret_cast<const uint32_t*>(sm.map + (lrow >> 1) * 8 + lhalf * 4);
-            mc = *reinterpret_cast<const uint32_t*>(sm.map + crow * 8 + lhalf * 4);
-        }
-        const bool l_uni = ml == (ml & 255u) * 0x01010101u, c_uni = mc == (mc & 255u) * 0x01010101u;
-        uint32_t y0, y1, c0;
-        if (st & 1u) {
-            const uint32_t bar = smem_u32(&sm.bar[i & (PIPE_NB - 1)]), par = (st >> 3) & 1u;
-            uint32_t done, spins = 0;
-            do {
-                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(par) : "memory");
-                if (!done && ++spins > (1u << 24)) __trap();   // a lost transaction must surface as an error, never as a hang
-            } while (!done);
-            const int set0 = (int)((st >> 1) & 3u);
-            if (l_uni) {
-                const int k = (int)(ml & 255u);
-                const PartV p = k ? p1 : p0;
-                tile_row8(sm.box[(set0 + k) & (PIPE_NB - 1)], (uint32_t)(lrow * 32 + ((mbx * 16 + (p.mvx >> 1)) & 15) + lhalf * 8), (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
-            } else {
-                uint32_t o[2] = {0, 0};
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int k = (int)((ml >> (8 * c)) & 255u);
-                    const PartV p = k ? p1 : p0;
-                    const uint8_t* t = sm.box[(set0 + k) & (PIPE_NB - 1)] + lrow * 32 + ((mbx * 16 + (p.mvx >> 1)) & 15) + lhalf * 8 + 2 * c;
-                    const int ph = (p.mvx & 1) | ((p.mvy & 1) << 1);
-                    o[c >> 1] |= (tile_px(t, 32, ph) | tile_px(t + 1, 32, ph) << 8) << (16 * (c & 1));
-                }
-                y0 = o[0]; y1 = o[1];
-            }
-            if (c_uni) {
-                const int k = (int)(mc & 255u);
-                const PartV p = k ? p1 : p0;
-                const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                c0 = tile_row4(sm.box[(set0 + k) & (PIPE_NB - 1)] + 640 + cpl * 384, (uint32_t)(crow * 32 + ((mbx * 8 + (cx >> 1)) & 15) + lhalf * 4), (cx & 1) | ((cy & 1) << 1));
-            } else {
-                c0 = 0;
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int k = (int)((mc >> (8 * c)) & 255u);
-                    const PartV p = k ? p1 : p0;
-                    const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                    c0 |= tile_px(sm.box[(set0 + k) & (PIPE_NB - 1)] + 640 + cpl * 384 + crow * 32 + ((mbx * 8 + (cx >> 1)) & 15) + lhalf * 4 + c, 32, (cx & 1) | ((cy & 1) << 1)) << (8 * c);
-                }
-            }
-            __syncwarp();          // every lane has read the boxes: the producer may refill them
-            freesets += n_parts;
-        } else {
-            auto leaf = [&](uint32_t idx) { return idx == 0 ? p0 : leaf_at(pbase + idx); };
-            if (l_uni) {
-                const PartV p = leaf(ml & 255u);
-                mc_row8(J.ref[p.ref - 1] + ypix + ((p.mvy >> 1) << LOG2S) + (p.mvx >> 1), S, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
-            } else {
-                uint32_t o[2] = {0, 0};
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const PartV p = leaf((ml >> (8 * c)) & 255u);
-                    const uint8_t* s = J.ref[p.ref - 1] + ypix + 2 * c + ((p.mvy >> 1) << LOG2S) + (p.mvx >> 1);
-                    const int ph = (p.mvx & 1) | ((p.mvy & 1) << 1);
-                    const uint32_t v = mc_px(s, S, ph) | mc_px(s + 1, S, ph) << 8;
-                    o[c >> 1] |= v << (16 * (c & 1));
-                }
-                y0 = o[0]; y1 = o[1];
-            }
-            if (c_uni) {
-                const PartV p = leaf(mc & 255u);
-                const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                c0 = mc_row4(J.ref[p.ref - 1] + ysz + cpix + ((cy >> 1) << LOG2S) + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1));
-            } else {
-                c0 = 0;
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const PartV p = leaf((mc >> (8 * c)) & 255u);
-                    const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                    c0 |= mc_px(J.ref[p.ref - 1] + ysz + cpix + c + ((cy >> 1) << LOG2S) + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1)) << (8 * c);
-                }
-            }
-        }
-
-        if (n_coef) {
-            // ---- dequantise into the compacted coefficient blocks (MD:3424-3429) ----
-            const int nblk = __popc(blkmask);
-            __syncwarp();   // the previous macroblock's final tile reads are done
-            for (int k = lane; k < nblk * 16; k += 32) reinterpret_cast<int4*>(&sm.coef[0][0])[k] = make_int4(0, 0, 0, 0);
-            *reinterpret_cast<uint2*>(sm.tile + lrow * 16 + lhalf * 8) = make_uint2(y0, y1);
-            *reinterpret_cast<uint32_t*>(sm.tile + 256 + cpl * 64 + crow * 8 + lhalf * 4) = c0;
-            __syncwarp();
-            uint32_t m8 = 0;
-            for (int j = lane; j < n_coef; j += 32) {
-                const uint32_t c = j < 32 ? c_first : __ldg(cf + dz + j);
-                const int level = (int)(int16_t)(c & 0xFFFFu);
-                const uint32_t pos = (c >> 16) & 63u, sub = (c >> 22) & 3u, blk = (c >> 24) & 7u, is8 = c >> 31;
-                const uint32_t w = sm.qtab[is8 ? pos : 64u + (pos & 15u)];
-                const uint32_t slot = __popc(blkmask & ((1u << blk) - 1u));
-                sm.coef[slot][is8 ? (w & 63u) : sub * 16u + (w & 15u)] = (int)(w >> 8) * level;
-                m8 |= is8 << blk;
-            }
-            m8 = __reduce_or_sync(0xffffffffu, m8);
-            const uint32_t list = c_blklist[blkmask];   // ids of the coded blocks, one nibble each, in slot order
-            __syncwarp();
-            // inverse transforms: eight lanes per coded block (one row each), four blocks per pass
-            const int g = lane >> 3, r = lane & 7, i4 = r & 3, s0 = (r >> 2) * 2;
-            for (int base = 0; base < nblk; base += 4) {
-                const int slot = base + g;
-                const bool has = slot < nblk;
-                const int b = (int)((list >> (4 * slot)) & 7u);
-                const bool is8 = (m8 >> b) & 1u;
-                int32_t* B = sm.coef[has ? slot : 0];
-                int32_t in[8], v[8];
-                if (has) {
-                    const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r : s0 * 16 + 4 * i4));
-                    const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r + 4 : (s0 + 1) * 16 + 4 * i4));
-                    in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
-                    if (is8) { if (r == 0) in[0] += 32; bfly8(in, v); }
-                    else { if (i4 == 0) { in[0] += 32; in[4] += 32; } bfly4(in, v); bfly4(in + 4, v + 4); }
-                }
-                __syncwarp();
-                if (has) {
-                    if (is8) {
-#pragma unroll
-                        for (int k = 0; k < 8; k++) B[8 * k + r] = v[k];
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) { B[s0 * 16 + 4 * k + i4] = v[k]; B[(s0 + 1) * 16 + 4 * k + i4] = v[4 + k]; }
-                    }
-                }
-                __syncwarp();
-                if (has) {
-                    const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r : s0 * 16 + 4 * i4));
-                    const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r + 4 : (s0 + 1) * 16 + 4 * i4));
-                    in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
-                    if (is8) bfly8(in, v); else { bfly4(in, v); bfly4(in + 4, v + 4); }
-                    uint8_t* t = b < 4 ? sm.tile + ((b >> 1) * 8 + r) * 16 + (b & 1) * 8 : sm.tile + 256 + (b - 4) * 64 + r * 8;
-                    uint2 px = *reinterpret_cast<uint2*>(t);
-                    px.x = addsat4(px.x, v[0], v[1], v[2], v[3]);
-                    px.y = addsat4(px.y, v[4], v[5], v[6], v[7]);
-                    *reinterpret_cast<uint2*>(t) = px;
-                }
-                __syncwarp();
-            }
-            const uint2 yy = *reinterpret_cast<const uint2*>(sm.tile + lrow * 16 + lhalf * 8);
-            y0 = yy.x; y1 = yy.y;
-            c0 = *reinterpret_cast<const uint32_t*>(sm.tile + 256 + cpl * 64 + crow * 8 + lhalf * 4);
-        }
-        *reinterpret_cast<uint2*>(J.dst + ypix) = make_uint2(y0, y1);
-        *reinterpret_cast<uint32_t*>(J.dst + ysz + cpix) = c0;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // intra macroblocks
 // ------------------------------------------------------------------------------------------------
 // Per-warp shared state.  Pixel tiles: luma rows y-1..y+15, columns x-4..x+27 (column x at index 4, so x-1 = 3 and
@@ -1192,18 +877,10 @@ cudaError_t init_kernel_tables() {
     return cudaMemcpyToSymbol(c_blklist, lut, sizeof lut);
 }
 
-cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, bool pipelined, cudaStream_t st) {
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, cudaStream_t st) {
     if (n_jobs <= 0) return cudaSuccess;
     dim3 grid((unsigned)((g.mbw * g.mbh + INTER_WARPS - 1) / INTER_WARPS), (unsigned)n_jobs);
     const uint32_t magic = (uint32_t)((0x100000000ull + (uint64_t)g.mbw - 1) / (uint64_t)g.mbw);
-    if (pipelined) {
-        const int per_cta = PIPE_WARPS * PIPE_RUN;
-        dim3 pgrid((unsigned)((g.mbw * g.mbh + per_cta - 1) / per_cta), (unsigned)n_jobs);
-        if (g.log2S == 8) k_inter_pipe<8><<<pgrid, PIPE_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
-        else if (g.log2S == 9) k_inter_pipe<9><<<pgrid, PIPE_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
-        else k_inter_pipe<10><<<pgrid, PIPE_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
-        return cudaGetLastError();
-    }
     if (g.log2S == 8) k_inter<8><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
     else if (g.log2S == 9) k_inter<9><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
     else k_inter<10><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);

@@ -36,8 +36,7 @@ struct Geom {
 cudaError_t init_kernel_tables();
 // Inter macroblocks of every job: MC from the ring + dequant/IDCT/add/clip.  One warp per MB.
 // tm_l / tm_c: the ring as a rank-3 u8 tensor (Stride, 1.5*H, pictures) with boxes 32x17x1 (luma windows) and 32x9x1 (chroma windows).
-// pipelined: k_inter_pipe (one warp per run of 16 macroblocks, TMA boxes in flight ahead) instead of k_inter (one warp per macroblock).
-cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, bool pipelined, cudaStream_t st);
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, cudaStream_t st);
 // Intra macroblocks (I-frames and intra MBs of P-frames) as a dependency wavefront.  One warp per MB; work is handed
 // out through an atomic ticket in dependency-depth order so that a waiting warp's dependencies are always running.
 // *warps_launched receives the number of warps started: each draws exactly one ticket past n_work, so the

@@ -197,7 +197,6 @@ public:
         if (!ok(cudaMallocHost(&ptr_h_, sizeof(void*) * (size_t)N_), "cudaMallocHost(ptrs)")) return MOBI_ERR_NOMEM;
         if (!ok(init_kernel_tables(), "init_kernel_tables")) return MOBI_ERR_CUDA;
         if (!ok(cudaStreamSynchronize(stream_), "init sync")) return MOBI_ERR_CUDA;
-        if (const char* e = std::getenv("MOBI_INTER_KERNEL")) pipelined_ = std::strcmp(e, "pipe") == 0;
         return make_tensor_maps();
     }
     // The ring as one rank-3 u8 tensor (Stride, 1.5*H, pictures): a picture's chroma rows follow its luma rows at the
@@ -728,7 +727,7 @@ private:
         }
         if (L.n_inter_jobs) {
             if (timing_) tick(0, stream_);
-            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_l_, tm_c_, pipelined_, stream_), "k_inter")) return MOBI_ERR_CUDA;
+            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_l_, tm_c_, stream_), "k_inter")) return MOBI_ERR_CUDA;
             if (timing_) tick(0, stream_);
             stats_.launches++;
         }
@@ -825,7 +824,6 @@ private:
     uint32_t* ticket_ = nullptr;
     uint32_t ticket_base_ = 0, stamp_ = 0, key_resident_ = 0;   // ticket_[0]: work tickets of k_intra; ticket_[32]: resident I-picture CTAs
     CUtensorMap tm_l_, tm_c_;
-    bool pipelined_ = false;  // MOBI_INTER_KERNEL=pipe selects k_inter_pipe (one warp per run of 16 macroblocks; measured slower)
     cudaStream_t side_ = nullptr, copy_ = nullptr;
     cudaEvent_t fork_ = nullptr, join_ = nullptr;
     std::vector<std::vector<uint16_t>> depth_;
