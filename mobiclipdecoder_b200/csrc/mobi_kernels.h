@@ -36,7 +36,9 @@ struct Geom {
 cudaError_t init_kernel_tables();
 // Inter macroblocks of every job: MC from the ring + dequant/IDCT/add/clip.  One warp per MB.
 // tm_l / tm_c: the ring as a rank-3 u8 tensor (Stride, 1.5*H, pictures) with boxes 32x17x1 (luma windows) and 32x9x1 (chroma windows).
-cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, cudaStream_t st);
+// tm_c4: the ring as a rank-4 u8 tensor (Stride/2, 2, 1.5*H, pictures) -- each row split into its U and V halves -- with
+// box 32x2x9x1: the U and the V window of a leaf in one fetch.
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, const CUtensorMap& tm_c4, cudaStream_t st);
 // Intra macroblocks (I-frames and intra MBs of P-frames) as a dependency wavefront.  One warp per MB; work is handed
 // out through an atomic ticket in dependency-depth order so that a waiting warp's dependencies are always running.
 // *warps_launched receives the number of warps started: each draws exactly one ticket past n_work, so the

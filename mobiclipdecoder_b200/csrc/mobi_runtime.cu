@@ -217,6 +217,15 @@ public:
         if (r == CUDA_SUCCESS)
             r = encode(&tm_c_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ring_, dims, strides, box_c, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) {
+            // each row as (U half, V half): one 32x2x9 box holds both chroma windows of a leaf
+            const cuuint64_t dims4[4] = {(cuuint64_t)g_.S / 2, 2, (cuuint64_t)H_ * 3 / 2, (cuuint64_t)N_ * RING};
+            const cuuint64_t strides4[3] = {(cuuint64_t)g_.S / 2, (cuuint64_t)g_.S, (cuuint64_t)pic_};
+            const cuuint32_t estr4[4] = {1, 1, 1, 1};
+            const cuuint32_t box_c4[4] = {32, 2, 9, 1};
+            r = encode(&tm_c4_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, ring_, dims4, strides4, box_c4, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         if (r != CUDA_SUCCESS) return set_err(MOBI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
         return MOBI_OK;
     }
@@ -727,7 +736,7 @@ private:
         }
         if (L.n_inter_jobs) {
             if (timing_) tick(0, stream_);
-            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_l_, tm_c_, stream_), "k_inter")) return MOBI_ERR_CUDA;
+            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_l_, tm_c_, tm_c4_, stream_), "k_inter")) return MOBI_ERR_CUDA;
             if (timing_) tick(0, stream_);
             stats_.launches++;
         }
@@ -823,7 +832,7 @@ private:
     uint32_t* flags_ = nullptr;
     uint32_t* ticket_ = nullptr;
     uint32_t ticket_base_ = 0, stamp_ = 0, key_resident_ = 0;   // ticket_[0]: work tickets of k_intra; ticket_[32]: resident I-picture CTAs
-    CUtensorMap tm_l_, tm_c_;
+    CUtensorMap tm_l_, tm_c_, tm_c4_;
     cudaStream_t side_ = nullptr, copy_ = nullptr;
     cudaEvent_t fork_ = nullptr, join_ = nullptr;
     std::vector<std::vector<uint16_t>> depth_;
