@@ -741,6 +741,341 @@ k_inter_run(const DevJob* __restrict__ jobs, int mbw, uint32_t mbw_magic, int H,
 }
 
 // ------------------------------------------------------------------------------------------------
+// inter macroblocks, persistent chunk kernel: warps draw chunks of 16 consecutive macroblocks (four runs of four)
+// ------------------------------------------------------------------------------------------------
+// k_inter_run's CTAs live for about 1700 instructions per warp: CTA turnover and uneven warps inside a CTA leave a third of
+// the warp slots empty, and every run starts with two dependent trips to memory (job table, then descriptors).  Here the
+// grid is sized to the machine, warps draw chunks through an atomic ticket (the next ticket is requested before the
+// current chunk is worked on), lanes 0..15 decode the chunk's 16 descriptors at once, and the four runs of the chunk then
+// go through the same steps as in k_inter_run with their per-macroblock facts arriving by shuffle.
+constexpr int CH_WARPS = 4, CH_MBS = 16;
+
+// Window facts of one leaf as the prediction step wants them, 12 bits: column of the window inside its 16-byte-aligned
+// box (4), luma half-pel phase (2), the same for the chroma window (4 + 2).
+__device__ __forceinline__ uint32_t leaf_word(int x0, int cx0, int mvx, int mvy) {
+    return (uint32_t)(x0 & 15) | (uint32_t)((mvx & 1) | ((mvy & 1) << 1)) << 4 | (uint32_t)(cx0 & 15) << 6
+         | (uint32_t)(((mvx >> 1) & 1) | (((mvy >> 1) & 1) << 1)) << 10;
+}
+// mcw, the per-macroblock word that travels by shuffle: bits 0-11 leaf 0, 12-23 leaf 1, then
+constexpr uint32_t MCW_INTER = 1u << 24, MCW_BOX = 1u << 25, MCW_TWO = 1u << 26, MCW_LR = 1u << 27, MCW_SWAP = 1u << 30;   // bits 28-29: first box slot
+
+template <int LOG2S>
+__global__ void __launch_bounds__(CH_WARPS * 32, 7)
+k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, uint32_t cpp_magic, int mbw, uint32_t mbw_magic, int H,
+              uint32_t* __restrict__ ticket, uint32_t ticket_base,
+              const __grid_constant__ CUtensorMap tm_l, const __grid_constant__ CUtensorMap tm_c4) {
+    constexpr int RUN = 4;
+    using Smem = RunSmem<RUN>;
+    __shared__ __align__(128) Smem s_all[CH_WARPS];
+    constexpr int S = 1 << LOG2S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Smem& sm = s_all[warp];
+    uint8_t* const raw = sm.u.raw;
+    const size_t ysz = (size_t)S * H;
+    if (lane < RUN) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&sm.bar[lane])) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phases = 0;   // bit i: parity of the phase barrier i completes next
+    const int lrow = lane >> 1, lhalf = lane & 1;
+    const int cpl = lane >> 4, crow = (lane >> 1) & 7;
+    const int k16 = lane & 15, k4 = lane & 3;
+
+    uint32_t t = 0;
+    if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
+    t = __shfl_sync(0xffffffffu, t, 0) - ticket_base;
+    while (t < n_chunks) {
+        uint32_t t_next = 0;   // requested now, looked at when this chunk is done
+        if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t_next) : "l"(ticket) : "memory");
+        const uint32_t job = __umulhi(t, cpp_magic), chunk = t - job * cpp;
+        const DevJob& J = jobs[job];
+        const uint32_t n_mb = J.n_mb;
+        if (J.n_intra != n_mb) {   // an I-picture has nothing for this kernel
+            // ---- lane-parallel set-up: lanes l and l + 16 look after macroblock mbc + l ----
+            const uint32_t mbc = chunk * CH_MBS;
+            const bool in = mbc + k16 < n_mb;
+            const uint32_t mbk = in ? mbc + k16 : n_mb - 1;
+            const uint4 d = __ldg(reinterpret_cast<const uint4*>(J.mbs + mbk));
+            const uint32_t* const coefs = reinterpret_cast<const uint32_t*>(J.coefs);
+            const uint32_t* const qtab = J.hdr->qtab;
+            if (lane < 20) asm volatile("prefetch.global.L1 [%0];" :: "l"(qtab + lane * 4));   // the picture's 80 dequantisation words
+            uint8_t* const dst = J.dst;
+            const bool inter = in && !(d.x & 3u);
+            const uint32_t n_parts_k = (d.x >> 2) & 127u;
+            const uint32_t n_coef = inter ? (d.x >> 9) & 511u : 0u;
+            const uint32_t bm = inter ? (d.x >> 18) & 63u : 0u;
+            const int mby = (int)__umulhi(mbk, mbw_magic), mbx = (int)mbk - mby * mbw;
+            const int yoff = ((mby * 16) << LOG2S) + mbx * 16;
+            // leaves 0 and 1: the inline copy of an unsplit macroblock's single leaf (info bit 28), else the records; lanes
+            // 16..31 fetch leaves 2 and 3 of the same macroblock for the load-per-lane path
+            const bool inl = n_parts_k == 1u && (d.x & (1u << 28));
+            uint2 pp0 = make_uint2(0u, 0u), pp1 = make_uint2(0u, 0u);
+            if (inter && !inl) {
+                const uint32_t q = (uint32_t)(lane >> 4) * 2u;
+                const uint2* pr = reinterpret_cast<const uint2*>(J.parts + d.y);
+                if (q < n_parts_k) pp0 = __ldg(pr + q);
+                if (q + 1u < n_parts_k) pp1 = __ldg(pr + q + 1u);
+            }
+            int mvx0, mvy0, ref0;
+            if (inl) { mvx0 = ((int)(d.w << 18)) >> 18; mvy0 = ((int)(d.w << 4)) >> 18; ref0 = (int)(d.w >> 28); }
+            else { const PartV v = part_of(pp0.x, pp0.y); mvx0 = v.mvx; mvy0 = v.mvy; ref0 = v.ref; }
+            const PartV v1 = part_of(pp1.x, pp1.y);
+            // boxes only when every column the windows need lies inside its own pixel row (flat addressing wraps, TMA zero-fills)
+            const int x00 = mbx * 16 + (mvx0 >> 1), cx00 = mbx * 8 + (mvx0 >> 2);
+            const int x01 = mbx * 16 + (v1.mvx >> 1), cx01 = mbx * 8 + (v1.mvx >> 2);
+            const bool row0 = x00 >= 0 && x00 + 17 <= S && cx00 >= 0 && cx00 + 9 <= (S >> 1);
+            const bool row1 = x01 >= 0 && x01 + 17 <= S && cx01 >= 0 && cx01 + 9 <= (S >> 1);
+            uint32_t need = 0;   // box slots wanted: 1 unsplit, 2 split once (16x8 + 16x8 or 8x16 + 8x16: each leaf fetches the whole window at its vector)
+            if (inter && lane < 16) {
+                if (n_parts_k == 1u && row0) need = 1;
+                else if (n_parts_k == 2u && row0 && row1) need = 2;
+            }
+            // first slot: running sum over the four macroblocks of the run; who does not fit takes the load-per-lane path
+            uint32_t incl = need;
+            { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, 1); if (k4 >= 1) incl += u; }
+            { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, 2); if (k4 >= 2) incl += u; }
+            const uint32_t slot0 = incl - need;
+            if (incl > (uint32_t)RUN) need = 0;   // (later macroblocks of the run keep the slots they counted on)
+            // an unsplit macroblock that goes down the load-per-lane path after all: its leaf record, rebuilt from the inline copy
+            if (inl && need == 0u) pp0 = make_uint2((0xFu | (uint32_t)ref0 << 4) << 8 | (uint32_t)mvx0 << 16, (uint32_t)mvy0 & 0xFFFFu);
+            const uint32_t mcw = leaf_word(x00, cx00, mvx0, mvy0) | leaf_word(x01, cx01, v1.mvx, v1.mvy) << 12 | (inter ? MCW_INTER : 0u)
+                               | (need ? MCW_BOX : 0u) | (need == 2u ? MCW_TWO : 0u) | (((pp0.x | pp1.x) & 15u) ? MCW_LR : 0u) | ((pp0.x & 255u) ? MCW_SWAP : 0u) | (slot0 & 3u) << 28;
+            int pic0 = 0, pic1 = 0;
+            if (need) pic0 = (int)J.ref_pic[ref0 - 1];
+            if (need == 2u) pic1 = (int)J.ref_pic[v1.ref - 1];
+
+#pragma unroll 1
+            for (int r = 0; r < CH_MBS / RUN; r++) {
+                if (mbc + (uint32_t)(RUN * r) >= n_mb) break;
+                const int l0 = RUN * r;              // lanes l0 .. l0+3 hold this run's macroblocks
+                const bool mine = (k16 >> 2) == r;
+                // everyone is done with the previous run's shared memory; its generic-proxy traffic is ordered before the boxes
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane >= l0 && lane < l0 + RUN && need) {
+                    const uint32_t bar = smem_u32(&sm.bar[k4]);
+                    const uint32_t s0 = (mcw >> 28) & 3u;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(need * (TMA_BYTES_L + TMA_BYTES_C4)) : "memory");
+                    tma_load_3d(smem_u32(raw + s0 * 640), &tm_l, x00 & ~15, mby * 16 + (mvy0 >> 1), pic0, bar);
+                    tma_load_4d(smem_u32(raw + RUN * 640 + s0 * 640), &tm_c4, cx00 & ~15, 0, H + mby * 8 + (mvy0 >> 2), pic0, bar);
+                    if (need == 2u) {
+                        tma_load_3d(smem_u32(raw + (s0 + 1u) * 640), &tm_l, x01 & ~15, mby * 16 + (v1.mvy >> 1), pic1, bar);
+                        tma_load_4d(smem_u32(raw + RUN * 640 + (s0 + 1u) * 640), &tm_c4, cx01 & ~15, 0, H + mby * 8 + (v1.mvy >> 2), pic1, bar);
+                    }
+                }
+                // the run's coefficient records: one range of the picture's array; the first 64 are fetched now
+                const uint32_t jmin = __reduce_min_sync(0xffffffffu, mine && n_coef ? d.z : 0xffffffffu);
+                const uint32_t jmax = __reduce_max_sync(0xffffffffu, mine && n_coef ? d.z + n_coef : 0u);
+                const uint32_t ntot = jmax > jmin ? jmax - jmin : 0u;
+                const uint32_t* cf = coefs + (ntot ? jmin : 0u);
+                uint32_t ca = 0, cb = 0;
+                if ((uint32_t)lane < ntot) ca = __ldg(cf + lane);
+                if ((uint32_t)lane + 32u < ntot) cb = __ldg(cf + 32 + lane);
+                const uint32_t bmp = __reduce_or_sync(0xffffffffu, mine ? bm << (8 * k4) : 0u);   // the run's coded-block masks, one byte each
+
+                // ---- prediction, one macroblock at a time, into its tile ----
+#pragma unroll 1
+                for (int i = 0; i < RUN; i++) {
+                    const uint32_t w = __shfl_sync(0xffffffffu, mcw, l0 + i);
+                    if (!(w & MCW_INTER)) continue;   // intra (k_intra's job) or past the picture's last macroblock
+                    uint32_t y0, y1, c0;
+                    if (w & MCW_BOX) {
+                        const uint32_t bar = smem_u32(&sm.bar[i]), par = (phases >> i) & 1u;
+                        phases ^= 1u << i;
+                        uint32_t done, spins = 0;
+                        do {
+                            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(par) : "memory");
+                            if (!done && ++spins > (1u << 22)) __trap();   // a box that never arrives must not hang the device
+                        } while (!done);
+                        // which leaf covers this lane's pixels: split top/bottom -> by row, left/right -> by half (luma 8, chroma 4 pixels per lane)
+                        uint32_t sl = 0, sc = 0;
+                        if (w & MCW_TWO) {   // leaf 0 is the top / left half unless the records come in the other order
+                            const uint32_t sw = (w >> 30) & 1u;
+                            sl = ((w & MCW_LR) ? (uint32_t)lhalf : (uint32_t)(lrow >> 3)) ^ sw;
+                            sc = ((w & MCW_LR) ? (uint32_t)lhalf : (uint32_t)(crow >> 2)) ^ sw;
+                        }
+                        const uint32_t s0 = (w >> 28) & 3u;
+                        const uint32_t wl = sl ? w >> 12 : w, wc = sc ? w >> 12 : w;
+                        tile_row8(raw + (s0 + sl) * 640, (uint32_t)(lrow * 32 + lhalf * 8) + (wl & 15u), (int)((wl >> 4) & 3u), y0, y1);
+                        c0 = tile_row4_p64(raw + RUN * 640 + (s0 + sc) * 640, (uint32_t)((crow * 2 + cpl) * 32 + lhalf * 4) + ((wc >> 6) & 15u), (int)((wc >> 10) & 3u));
+                    } else {
+                        // load-per-lane path (CopyBlock MD:418-456 on the flat planes)
+                        const uint32_t dx = __shfl_sync(0xffffffffu, d.x, l0 + i), dy = __shfl_sync(0xffffffffu, d.y, l0 + i);
+                        const int yo = __shfl_sync(0xffffffffu, yoff, l0 + i);
+                        const int n_parts = (int)((dx >> 2) & 127u);
+                        uint2* sp = reinterpret_cast<uint2*>(raw + Smem::BOX);
+                        uint8_t* map = raw + Smem::BOX + 512;
+                        // leaves 0..3 were fetched with the descriptors (lanes l0+i and 16+l0+i hold them), the rest is fetched now
+                        if (k16 == l0 + i) { sp[(lane >> 4) * 2] = pp0; sp[(lane >> 4) * 2 + 1] = pp1; }
+                        const mobi_part* parts = J.parts + dy;
+                        for (int p = 4 + lane; p < n_parts; p += 32) sp[p] = __ldg(reinterpret_cast<const uint2*>(parts + p));
+                        __syncwarp();
+                        uint32_t ml = 0, mc = 0;
+                        if (n_parts > 1) {
+                            // partition map at 2x2-pixel granularity (leaves go down to 2x2, MD:1726): lane l owns cells 2l, 2l+1 of the 8x8 grid
+                            const int cy2 = lane >> 2, cx2 = (lane & 3) * 2;
+                            uint32_t i0 = 0, i1 = 0;
+                            for (int p = 0; p < n_parts; p++) {
+                                const uint32_t pw = sp[p].x;
+                                const int x2 = pw & 15, y2 = (pw >> 4) & 15, cw = 1 << ((pw >> 8) & 3), ch = 1 << ((pw >> 10) & 3);
+                                const bool rowin = (unsigned)(cy2 - y2) < (unsigned)ch;
+                                if (rowin && (unsigned)(cx2 - x2) < (unsigned)cw) i0 = (uint32_t)p;
+                                if (rowin && (unsigned)(cx2 + 1 - x2) < (unsigned)cw) i1 = (uint32_t)p;
+                            }
+                            reinterpret_cast<uint16_t*>(map)[lane] = (uint16_t)(i0 | i1 << 8);
+                            __syncwarp();
+                            ml = *reinterpret_cast<const uint32_t*>(map + (lrow >> 1) * 8 + lhalf * 4);
+                            mc = *reinterpret_cast<const uint32_t*>(map + crow * 8 + lhalf * 4);
+                        }
+                        const int ypix = yo + (lrow << LOG2S) + lhalf * 8;
+                        const int cpix = (yo >> 1) + (cpl ? (S >> 1) : 0) + (crow << LOG2S) + lhalf * 4;
+                        auto leaf = [&](uint32_t idx) { const uint2 pw = sp[idx]; return part_of(pw.x, pw.y); };
+                        if (ml == (ml & 255u) * 0x01010101u) {
+                            const PartV p = leaf(ml & 255u);
+                            mc_row8(J.ref[p.ref - 1] + ypix + ((p.mvy >> 1) << LOG2S) + (p.mvx >> 1), S, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
+                        } else {
+                            uint32_t o[2] = {0, 0};
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                const PartV p = leaf((ml >> (8 * c)) & 255u);
+                                const uint8_t* s = J.ref[p.ref - 1] + ypix + 2 * c + ((p.mvy >> 1) << LOG2S) + (p.mvx >> 1);
+                                const int ph = (p.mvx & 1) | ((p.mvy & 1) << 1);
+                                const uint32_t v = mc_px(s, S, ph) | mc_px(s + 1, S, ph) << 8;
+                                o[c >> 1] |= v << (16 * (c & 1));
+                            }
+                            y0 = o[0]; y1 = o[1];
+                        }
+                        if (mc == (mc & 255u) * 0x01010101u) {
+                            const PartV p = leaf(mc & 255u);
+                            const int cx = p.mvx >> 1, cy = p.mvy >> 1;
+                            c0 = mc_row4(J.ref[p.ref - 1] + ysz + cpix + ((cy >> 1) << LOG2S) + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1));
+                        } else {
+                            c0 = 0;
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                const PartV p = leaf((mc >> (8 * c)) & 255u);
+                                const int cx = p.mvx >> 1, cy = p.mvy >> 1;
+                                c0 |= mc_px(J.ref[p.ref - 1] + ysz + cpix + c + ((cy >> 1) << LOG2S) + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1)) << (8 * c);
+                            }
+                        }
+                        __syncwarp();   // everyone is done with the leaf records before the next split macroblock replaces them
+                    }
+                    uint8_t* tl = sm.tile[i];
+                    *reinterpret_cast<uint2*>(tl + lrow * 16 + lhalf * 8) = make_uint2(y0, y1);
+                    *reinterpret_cast<uint32_t*>(tl + 256 + cpl * 64 + crow * 8 + lhalf * 4) = c0;
+                }
+                __syncwarp();   // tiles complete; the boxes are dead, the coefficient pool may overwrite them
+
+                if (ntot) {
+                    // ---- pool slots: macroblock i's coded blocks take slots sb_i .. sb_i + popc(mask_i) - 1, lowest block first ----
+                    uint32_t sbp = 0, ns = 0;
+#pragma unroll
+                    for (int i = 0; i < RUN; i++) { sbp |= ns << (8 * i); ns += __popc((bmp >> (8 * i)) & 63u); }
+                    {
+                        int4* z = reinterpret_cast<int4*>(&sm.u.coef[0][0]);
+                        for (uint32_t q = lane; q < ns * 16u; q += 32u) z[q] = make_int4(0, 0, 0, 0);
+                    }
+                    uint32_t st_i[RUN], n_i[RUN];
+#pragma unroll
+                    for (int i = 0; i < RUN; i++) { st_i[i] = __shfl_sync(0xffffffffu, d.z, l0 + i) - jmin; n_i[i] = __shfl_sync(0xffffffffu, n_coef, l0 + i); }
+                    __syncwarp();
+                    // ---- dequantise into the pool (MD:3424-3429) ----
+                    uint32_t m8 = 0;
+                    for (uint32_t j0 = 0; j0 < ntot; j0 += 32u) {
+                        const uint32_t j = j0 + (uint32_t)lane;
+                        if (j < ntot) {
+                            const uint32_t c = j0 == 0 ? ca : j0 == 32u ? cb : __ldg(cf + j);
+                            int own = -1;
+#pragma unroll
+                            for (int i = 0; i < RUN; i++) if (j - st_i[i] < n_i[i]) own = i;
+                            if (own >= 0) {
+                                const int level = (int)(int16_t)(c & 0xFFFFu);
+                                const uint32_t pos = (c >> 16) & 63u, sub = (c >> 22) & 3u, blk = (c >> 24) & 7u, is8 = c >> 31;
+                                const uint32_t wq = __ldg(qtab + (is8 ? pos : 64u + (pos & 15u)));
+                                const uint32_t mask = (bmp >> (8 * own)) & 63u;
+                                const uint32_t slot = ((sbp >> (8 * own)) & 255u) + __popc(mask & ((1u << blk) - 1u));
+                                sm.u.coef[slot][is8 ? (wq & 63u) : sub * 16u + (wq & 15u)] = (int)(wq >> 8) * level;
+                                m8 |= is8 << (8 * own + blk);
+                            }
+                        }
+                    }
+                    m8 = __reduce_or_sync(0xffffffffu, m8);
+                    if (lane < 6 * RUN) {
+                        const uint32_t kk = (uint32_t)lane / 6u, b = (uint32_t)lane - 6u * kk;
+                        const uint32_t mask = (bmp >> (8 * kk)) & 63u;
+                        if ((mask >> b) & 1u) {
+                            const uint32_t slot = ((sbp >> (8 * kk)) & 255u) + __popc(mask & ((1u << b) - 1u));
+                            const uint32_t toff = kk * 384u + (b < 4u ? ((b >> 1) * 8u) * 16u + (b & 1u) * 8u : 256u + (b - 4u) * 64u);
+                            sm.slotinfo[slot] = toff | (b < 4u ? 0u : 1u << 16) | ((m8 >> (8 * kk + b)) & 1u) << 17;
+                        }
+                    }
+                    __syncwarp();
+
+                    // ---- inverse transforms: eight lanes per pooled block (one row each), four blocks per pass ----
+                    const int g = lane >> 3, rr = lane & 7, i4 = rr & 3, s0 = (rr >> 2) * 2;
+                    for (uint32_t base = 0; base < ns; base += 4u) {
+                        const uint32_t slot = base + (uint32_t)g;
+                        const bool has = slot < ns;
+                        const uint32_t info = sm.slotinfo[has ? slot : 0u];
+                        const bool is8 = (info >> 17) & 1u;
+                        int32_t* B = sm.u.coef[has ? slot : 0u];
+                        int32_t in[8], v[8];
+                        if (has) {
+                            const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * rr : s0 * 16 + 4 * i4));
+                            const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * rr + 4 : (s0 + 1) * 16 + 4 * i4));
+                            in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
+                            if (is8) { if (rr == 0) in[0] += 32; bfly8(in, v); }
+                            else { if (i4 == 0) { in[0] += 32; in[4] += 32; } bfly4(in, v); bfly4(in + 4, v + 4); }
+                        }
+                        __syncwarp();
+                        if (has) {
+                            if (is8) {
+#pragma unroll
+                                for (int q = 0; q < 8; q++) B[8 * q + rr] = v[q];
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 4; q++) { B[s0 * 16 + 4 * q + i4] = v[q]; B[(s0 + 1) * 16 + 4 * q + i4] = v[4 + q]; }
+                            }
+                        }
+                        __syncwarp();
+                        if (has) {
+                            const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * rr : s0 * 16 + 4 * i4));
+                            const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * rr + 4 : (s0 + 1) * 16 + 4 * i4));
+                            in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
+                            if (is8) bfly8(in, v); else { bfly4(in, v); bfly4(in + 4, v + 4); }
+                            // either way the lane now holds the residuals of row rr, columns 0..7 of its block: add onto the prediction
+                            uint8_t* tp = &sm.tile[0][0] + (info & 0xFFFFu) + rr * ((info >> 16) & 1u ? 8 : 16);
+                            uint2 px = *reinterpret_cast<uint2*>(tp);
+                            px.x = addsat4(px.x, v[0], v[1], v[2], v[3]);
+                            px.y = addsat4(px.y, v[4], v[5], v[6], v[7]);
+                            *reinterpret_cast<uint2*>(tp) = px;
+                        }
+                        __syncwarp();
+                    }
+                }
+
+                // ---- the tiles leave, lane-parallel over the run again: 16 luma bytes / 8 chroma bytes per lane and round ----
+                const int yoff_k = __shfl_sync(0xffffffffu, yoff, l0 + k4);
+                const bool inter_k = (__shfl_sync(0xffffffffu, mcw, l0 + k4) & MCW_INTER) != 0u;
+                if (inter_k) {
+                    const uint8_t* tl = sm.tile[k4];
+                    uint8_t* const py = dst + yoff_k;
+                    uint8_t* const pc = dst + ysz + (yoff_k >> 1);
+#pragma unroll
+                    for (int row = lane / RUN; row < 16; row += 32 / RUN)
+                        *reinterpret_cast<uint4*>(py + (row << LOG2S)) = *reinterpret_cast<const uint4*>(tl + row * 16);
+#pragma unroll
+                    for (int q = lane / RUN; q < 16; q += 32 / RUN)
+                        *reinterpret_cast<uint2*>(pc + (q >> 3) * (S >> 1) + ((q & 7) << LOG2S)) = *reinterpret_cast<const uint2*>(tl + 256 + q * 8);
+                }
+            }
+        }
+        t = __shfl_sync(0xffffffffu, t_next, 0) - ticket_base;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // intra macroblocks
 // ------------------------------------------------------------------------------------------------
 // Per-warp shared state.  Pixel tiles: luma rows y-1..y+15, columns x-4..x+27 (column x at index 4, so x-1 = 3 and
@@ -1173,11 +1508,13 @@ cudaError_t init_kernel_tables() {
     return cudaMemcpyToSymbol(c_blklist, lut, sizeof lut);
 }
 
-// MOBI_INTER_KERNEL selects the inter kernel: "run4" / "run2" = k_inter_run with 4 / 2 macroblocks per warp, "warp" = k_inter.
+// MOBI_INTER_KERNEL selects the inter kernel: "chunk" = k_inter_chunk (persistent, tickets), "run4" / "run2" = k_inter_run with
+// 4 / 2 macroblocks per warp, "warp" = k_inter.
 static int inter_kernel_choice() {
     static const int choice = [] {
         const char* e = getenv("MOBI_INTER_KERNEL");
         if (!e || !*e) return 0;
+        if (!strcmp(e, "chunk")) return 16;
         if (!strcmp(e, "run4")) return 4;
         if (!strcmp(e, "run2")) return 2;
         return 0;
@@ -1194,10 +1531,23 @@ static void launch_inter_run(const DevJob* jobs, int n_jobs, Geom g, uint32_t ma
     else k_inter_run<10, RUN><<<grid, RUNK_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c4);
 }
 
-cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, const CUtensorMap& tm_c4, cudaStream_t st) {
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, const CUtensorMap& tm_c4,
+                         int sm_count, uint32_t* ticket, uint32_t ticket_base, uint32_t* tickets_drawn, cudaStream_t st) {
+    *tickets_drawn = 0;
     if (n_jobs <= 0) return cudaSuccess;
     const uint32_t magic = (uint32_t)((0x100000000ull + (uint64_t)g.mbw - 1) / (uint64_t)g.mbw);
     const int choice = inter_kernel_choice();
+    if (choice == 16) {
+        const uint32_t cpp = (uint32_t)((g.mbw * g.mbh + CH_MBS - 1) / CH_MBS), n_chunks = cpp * (uint32_t)n_jobs;
+        const uint32_t cpp_magic = (uint32_t)((0x100000000ull + (uint64_t)cpp - 1) / (uint64_t)cpp);
+        uint32_t ctas = (uint32_t)sm_count * 7u;
+        if (ctas > (n_chunks + CH_WARPS - 1) / CH_WARPS) ctas = (n_chunks + CH_WARPS - 1) / CH_WARPS;
+        if (g.log2S == 8) k_inter_chunk<8><<<ctas, CH_WARPS * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, ticket, ticket_base, tm_l, tm_c4);
+        else if (g.log2S == 9) k_inter_chunk<9><<<ctas, CH_WARPS * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, ticket, ticket_base, tm_l, tm_c4);
+        else k_inter_chunk<10><<<ctas, CH_WARPS * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, ticket, ticket_base, tm_l, tm_c4);
+        *tickets_drawn = n_chunks + ctas * CH_WARPS;   // every warp draws exactly one ticket past the end
+        return cudaGetLastError();
+    }
     if (choice == 4) { launch_inter_run<4>(jobs, n_jobs, g, magic, tm_l, tm_c4, st); return cudaGetLastError(); }
     if (choice == 2) { launch_inter_run<2>(jobs, n_jobs, g, magic, tm_l, tm_c4, st); return cudaGetLastError(); }
     dim3 grid((unsigned)((g.mbw * g.mbh + INTER_WARPS - 1) / INTER_WARPS), (unsigned)n_jobs);

@@ -38,7 +38,10 @@ cudaError_t init_kernel_tables();
 // tm_l / tm_c: the ring as a rank-3 u8 tensor (Stride, 1.5*H, pictures) with boxes 32x17x1 (luma windows) and 32x9x1 (chroma windows).
 // tm_c4: the ring as a rank-4 u8 tensor (Stride/2, 2, 1.5*H, pictures) -- each row split into its U and V halves -- with
 // box 32x2x9x1: the U and the V window of a leaf in one fetch.
-cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, const CUtensorMap& tm_c4, cudaStream_t st);
+// The persistent variant hands out chunks of 16 macroblocks through *ticket (monotonic, like launch_intra's): the next
+// launch's ticket_base is ticket_base + *tickets_drawn.
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, const CUtensorMap& tm_c4,
+                         int sm_count, uint32_t* ticket, uint32_t ticket_base, uint32_t* tickets_drawn, cudaStream_t st);
 // Intra macroblocks (I-frames and intra MBs of P-frames) as a dependency wavefront.  One warp per MB; work is handed
 // out through an atomic ticket in dependency-depth order so that a waiting warp's dependencies are always running.
 // *warps_launched receives the number of warps started: each draws exactly one ticket past n_work, so the

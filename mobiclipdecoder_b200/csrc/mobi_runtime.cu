@@ -736,7 +736,9 @@ private:
         }
         if (L.n_inter_jobs) {
             if (timing_) tick(0, stream_);
-            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_l_, tm_c_, tm_c4_, stream_), "k_inter")) return MOBI_ERR_CUDA;
+            uint32_t drawn = 0;
+            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_l_, tm_c_, tm_c4_, sm_count_, ticket_ + 16, inter_ticket_base_, &drawn, stream_), "k_inter")) return MOBI_ERR_CUDA;
+            inter_ticket_base_ += drawn;
             if (timing_) tick(0, stream_);
             stats_.launches++;
         }
@@ -831,7 +833,7 @@ private:
     uint8_t* ring_ = nullptr;
     uint32_t* flags_ = nullptr;
     uint32_t* ticket_ = nullptr;
-    uint32_t ticket_base_ = 0, stamp_ = 0, key_resident_ = 0;   // ticket_[0]: work tickets of k_intra; ticket_[32]: resident I-picture CTAs
+    uint32_t ticket_base_ = 0, inter_ticket_base_ = 0, stamp_ = 0, key_resident_ = 0;   // ticket_[0]: work tickets of k_intra; ticket_[16]: chunk tickets of k_inter_chunk; ticket_[32]: resident I-picture CTAs
     CUtensorMap tm_l_, tm_c_, tm_c4_;
     cudaStream_t side_ = nullptr, copy_ = nullptr;
     cudaEvent_t fork_ = nullptr, join_ = nullptr;

@@ -3,10 +3,10 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi -L; nproc
-for k in ${KERNELS:-run4 run2}; do
+for k in ${KERNELS:-chunk}; do
   echo "=== pytest -m gpu MOBI_INTER_KERNEL=$k"; MOBI_INTER_KERNEL=$k timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
 done
-for k in ${BENCH_KERNELS:-warp run4 run2}; do
+for k in ${BENCH_KERNELS:-chunk run2}; do
   echo "=== bench $k"; MOBI_INTER_KERNEL=$k timeout 400 python bench.py --no-e2e --no-cpu > gpurun_out/bench_$k.json 2> gpurun_out/bench_$k.err
   python - <<PY
 import json
@@ -17,11 +17,9 @@ except Exception as e:
     print('$k', 'bench failed', e); print(open('gpurun_out/bench_$k.err').read()[-1500:])
 PY
 done
-if [ "${NCU:-1}" = "1" ]; then
-for k in ${NCU_KERNELS:-warp run4}; do
+for k in ${NCU_KERNELS:-chunk}; do
   echo "=== ncu full $k"
-  MOBI_INTER_KERNEL=$k timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_inter' -s 3 -c 1 -f -o gpurun_out/prof_$k python bench.py --profile --steps 2 --warmup 2 > gpurun_out/ncu_full_$k.log 2>&1
+  MOBI_INTER_KERNEL=$k timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_inter' -s 2 -c 1 -f -o gpurun_out/prof_$k python bench.py --profile --steps 2 --warmup 2 > gpurun_out/ncu_full_$k.log 2>&1
   tail -2 gpurun_out/ncu_full_$k.log
 done
-fi
-ls -la gpurun_out
+ls -la gpurun_out | head -30
