@@ -447,22 +447,22 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, 7) k_inter(const DevJob* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// inter macroblocks, run kernel: one warp per RUN consecutive macroblocks
+// inter macroblocks, chunk kernel (the default): shared-memory layout and box helpers
 // ------------------------------------------------------------------------------------------------
 // What k_inter spends most of its issue slots on is work every lane of the warp repeats for its one macroblock
 // (descriptor decode, coordinates, eligibility, box addresses) and transform passes whose eight-lane groups are half
-// empty (1.8 coded 8x8 blocks per macroblock on the bench mix, four groups per pass).  Here a warp owns RUN consecutive
-// macroblocks of a picture:
-//   * set-up is lane-parallel: lane l decodes macroblock l % RUN; whatever is needed warp-wide later travels by shuffle;
-//   * lanes 0..RUN-1 issue their macroblock's boxes up front (one luma box, one rank-4 box holding the U and the V
-//     window), so RUN macroblocks' windows are in flight per warp;
+// empty (1.8 coded 8x8 blocks per macroblock on the bench mix, four groups per pass).  k_inter_chunk works on runs of
+// RUN = 4 consecutive macroblocks per warp:
+//   * set-up is lane-parallel: lane l decodes macroblock l of the chunk; whatever is needed warp-wide later travels by shuffle;
+//   * the lanes that hold a run's macroblocks issue their boxes up front (one luma box, one rank-4 box holding the U and
+//     the V window, per leaf), so a whole run's windows are in flight per warp;
 //   * prediction goes macroblock by macroblock into per-macroblock tiles in shared memory;
 //   * the coefficients of the whole run (one contiguous range of the picture's array) are dequantised together into
 //     one pool of block buffers (which reuse the space of the boxes), and the transform passes walk the pool, four coded
 //     blocks per pass regardless of which macroblock they belong to;
 //   * the tiles leave with 16-byte stores, lane-parallel over the macroblocks again.
-// Split macroblocks and windows that leave their pixel row (flat addressing wraps, TMA zero-fills) take a load-per-lane path.
-constexpr int RUNK_WARPS = 4;
+// Macroblocks with more than two leaves and windows that leave their pixel row (flat addressing wraps, TMA zero-fills)
+// take a load-per-lane path.
 constexpr uint32_t TMA_BYTES_C4 = 32 * 2 * 9;
 
 template <int RUN>
@@ -480,7 +480,8 @@ struct RunSmem {
     uint64_t bar[RUN];
     uint8_t pad[(128 - (REGION + RUN * 384 + SLOTS * 4 + RUN * 8) % 128) % 128];
 };
-static_assert(sizeof(RunSmem<4>) % 128 == 0 && sizeof(RunSmem<2>) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+static_assert(sizeof(RunSmem<4>) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+static_assert(sizeof(RunSmem<4>) * 4 + 1024 <= 233472 / 7, "seven 4-warp CTAs per SM");
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -498,256 +499,15 @@ __device__ __forceinline__ uint32_t tile_row4_p64(const uint8_t* base, uint32_t 
     return half4(half4(a0) + half4(b0)) + half4(half4(c0) + half4(d0));
 }
 
-template <int LOG2S, int RUN>
-__global__ void __launch_bounds__(RUNK_WARPS * 32, RUN == 4 ? 7 : 12)
-k_inter_run(const DevJob* __restrict__ jobs, int mbw, uint32_t mbw_magic, int H,
-            const __grid_constant__ CUtensorMap tm_l, const __grid_constant__ CUtensorMap tm_c4) {
-    using Smem = RunSmem<RUN>;
-    __shared__ __align__(128) Smem s_all[RUNK_WARPS];
-    constexpr int S = 1 << LOG2S;
-    const DevJob& J = jobs[blockIdx.y];
-    const uint32_t n_mb = J.n_mb;
-    if (J.n_intra == n_mb) return;  // I-picture: nothing for this kernel
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t mb0 = (blockIdx.x * RUNK_WARPS + warp) * RUN;
-    if (mb0 >= n_mb) return;
-    Smem& sm = s_all[warp];
-    uint8_t* const raw = sm.u.raw;
-    const size_t ysz = (size_t)S * H;
-
-    // ---- lane-parallel set-up: this lane looks after macroblock mb0 + k ----
-    const int k = lane & (RUN - 1);
-    const bool in = mb0 + k < n_mb;
-    const uint32_t mbk = in ? mb0 + k : n_mb - 1;
-    const uint4 d = __ldg(reinterpret_cast<const uint4*>(J.mbs + mbk));
-    const bool inter = in && !(d.x & 3u);
-    const uint32_t n_coef = inter ? (d.x >> 9) & 511u : 0u;
-    const uint32_t bm = inter ? (d.x >> 18) & 63u : 0u;
-    const int mby = (int)__umulhi(mbk, mbw_magic), mbx = (int)mbk - mby * mbw;   // exact for mb < 2^26
-    const int yoff = ((mby * 16) << LOG2S) + mbx * 16;
-    const int mvx = ((int)(d.w << 18)) >> 18, mvy = ((int)(d.w << 4)) >> 18;   // the inline leaf (info bit 28)
-    const int x0 = mbx * 16 + (mvx >> 1), cx0 = mbx * 8 + (mvx >> 2);
-    // boxes only when every column the windows need lies inside its own pixel row
-    const bool fast = inter && ((d.x >> 2) & 127u) == 1u && (d.x & (1u << 28)) && x0 >= 0 && x0 + 17 <= S && cx0 >= 0 && cx0 + 9 <= (S >> 1);
-    // what the prediction step needs to know, one word: window column inside the box and half-pel phase, luma and chroma
-    const uint32_t mcw = (uint32_t)(x0 & 15) | (uint32_t)((mvx & 1) | ((mvy & 1) << 1)) << 4 | (uint32_t)(cx0 & 15) << 8
-                       | (uint32_t)(((mvx >> 1) & 1) | (((mvy >> 1) & 1) << 1)) << 12 | (fast ? 1u << 16 : 0u) | (inter ? 1u << 17 : 0u);
-    if (lane < RUN) {
-        const uint32_t bar = smem_u32(&sm.bar[lane]);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (fast) {
-            const int pic = (int)J.ref_pic[(d.w >> 28) - 1u];
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(TMA_BYTES_L + TMA_BYTES_C4) : "memory");
-            tma_load_3d(smem_u32(raw + lane * 640), &tm_l, x0 & ~15, mby * 16 + (mvy >> 1), pic, bar);
-            tma_load_4d(smem_u32(raw + RUN * 640 + lane * 640), &tm_c4, cx0 & ~15, 0, H + mby * 8 + (mvy >> 2), pic, bar);
-        }
-    }
-    // the run's coefficient records: one range of the picture's array; the first 64 are fetched now
-    const uint32_t jmin = __reduce_min_sync(0xffffffffu, n_coef ? d.z : 0xffffffffu);
-    const uint32_t jmax = __reduce_max_sync(0xffffffffu, n_coef ? d.z + n_coef : 0u);
-    const uint32_t ntot = jmax > jmin ? jmax - jmin : 0u;
-    const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs) + (ntot ? jmin : 0u);
-    uint32_t ca = 0, cb = 0;
-    if ((uint32_t)lane < ntot) ca = __ldg(cf + lane);
-    if ((uint32_t)lane + 32u < ntot) cb = __ldg(cf + 32 + lane);
-    const uint32_t bmp = __reduce_or_sync(0xffffffffu, bm << (8 * k));   // the run's coded-block masks, one byte each
-    __syncwarp();   // barriers initialised before anyone polls them
-
-    // ---- prediction, one macroblock at a time, into its tile ----
-    const int lrow = lane >> 1, lhalf = lane & 1;
-    const int cpl = lane >> 4, crow = (lane >> 1) & 7;
-#pragma unroll 1
-    for (int i = 0; i < RUN; i++) {
-        const uint32_t w = __shfl_sync(0xffffffffu, mcw, i);
-        if (!(w & (1u << 17))) continue;   // intra (k_intra's job) or past the picture's last macroblock
-        uint32_t y0, y1, c0;
-        if (w & (1u << 16)) {
-            const uint32_t bar = smem_u32(&sm.bar[i]);
-            uint32_t done, spins = 0;
-            do {
-                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
-                if (!done && ++spins > (1u << 22)) __trap();   // a box that never arrives must not hang the device
-            } while (!done);
-            tile_row8(raw + i * 640, (uint32_t)(lrow * 32 + lhalf * 8) + (w & 15u), (int)((w >> 4) & 3u), y0, y1);
-            c0 = tile_row4_p64(raw + RUN * 640 + i * 640, (uint32_t)((crow * 2 + cpl) * 32 + lhalf * 4) + ((w >> 8) & 15u), (int)((w >> 12) & 3u));
-        } else {
-            // load-per-lane path (CopyBlock MD:418-456 on the flat planes)
-            const uint32_t dx = __shfl_sync(0xffffffffu, d.x, i), dy = __shfl_sync(0xffffffffu, d.y, i);
-            const int yo = __shfl_sync(0xffffffffu, yoff, i);
-            const int n_parts = (int)((dx >> 2) & 127u);
-            uint2* sp = reinterpret_cast<uint2*>(raw + Smem::BOX);
-            uint8_t* map = raw + Smem::BOX + 512;
-            const mobi_part* parts = J.parts + dy;
-            for (int p = lane; p < n_parts; p += 32) sp[p] = __ldg(reinterpret_cast<const uint2*>(parts + p));
-            __syncwarp();
-            uint32_t ml = 0, mc = 0;
-            if (n_parts > 1) {
-                // partition map at 2x2-pixel granularity (leaves go down to 2x2, MD:1726): lane l owns cells 2l, 2l+1 of the 8x8 grid
-                const int cy2 = lane >> 2, cx2 = (lane & 3) * 2;
-                uint32_t i0 = 0, i1 = 0;
-                for (int p = 0; p < n_parts; p++) {
-                    const uint32_t pw = sp[p].x;
-                    const int x2 = pw & 15, y2 = (pw >> 4) & 15, cw = 1 << ((pw >> 8) & 3), ch = 1 << ((pw >> 10) & 3);
-                    const bool rowin = (unsigned)(cy2 - y2) < (unsigned)ch;
-                    if (rowin && (unsigned)(cx2 - x2) < (unsigned)cw) i0 = (uint32_t)p;
-                    if (rowin && (unsigned)(cx2 + 1 - x2) < (unsigned)cw) i1 = (uint32_t)p;
-                }
-                reinterpret_cast<uint16_t*>(map)[lane] = (uint16_t)(i0 | i1 << 8);
-                __syncwarp();
-                ml = *reinterpret_cast<const uint32_t*>(map + (lrow >> 1) * 8 + lhalf * 4);
-                mc = *reinterpret_cast<const uint32_t*>(map + crow * 8 + lhalf * 4);
-            }
-            const int ypix = yo + (lrow << LOG2S) + lhalf * 8;
-            const int cpix = (yo >> 1) + (cpl ? (S >> 1) : 0) + (crow << LOG2S) + lhalf * 4;
-            auto leaf = [&](uint32_t idx) { const uint2 pw = sp[idx]; return part_of(pw.x, pw.y); };
-            if (ml == (ml & 255u) * 0x01010101u) {
-                const PartV p = leaf(ml & 255u);
-                mc_row8(J.ref[p.ref - 1] + ypix + ((p.mvy >> 1) << LOG2S) + (p.mvx >> 1), S, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
-            } else {
-                uint32_t o[2] = {0, 0};
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const PartV p = leaf((ml >> (8 * c)) & 255u);
-                    const uint8_t* s = J.ref[p.ref - 1] + ypix + 2 * c + ((p.mvy >> 1) << LOG2S) + (p.mvx >> 1);
-                    const int ph = (p.mvx & 1) | ((p.mvy & 1) << 1);
-                    const uint32_t v = mc_px(s, S, ph) | mc_px(s + 1, S, ph) << 8;
-                    o[c >> 1] |= v << (16 * (c & 1));
-                }
-                y0 = o[0]; y1 = o[1];
-            }
-            if (mc == (mc & 255u) * 0x01010101u) {
-                const PartV p = leaf(mc & 255u);
-                const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                c0 = mc_row4(J.ref[p.ref - 1] + ysz + cpix + ((cy >> 1) << LOG2S) + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1));
-            } else {
-                c0 = 0;
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const PartV p = leaf((mc >> (8 * c)) & 255u);
-                    const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                    c0 |= mc_px(J.ref[p.ref - 1] + ysz + cpix + c + ((cy >> 1) << LOG2S) + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1)) << (8 * c);
-                }
-            }
-            __syncwarp();   // everyone is done with the leaf records before the next split macroblock replaces them
-        }
-        uint8_t* t = sm.tile[i];
-        *reinterpret_cast<uint2*>(t + lrow * 16 + lhalf * 8) = make_uint2(y0, y1);
-        *reinterpret_cast<uint32_t*>(t + 256 + cpl * 64 + crow * 8 + lhalf * 4) = c0;
-    }
-    __syncwarp();   // tiles complete; the boxes are dead, the coefficient pool may overwrite them
-
-    if (ntot) {
-        // ---- pool slots: macroblock i's coded blocks take slots sb_i .. sb_i + popc(mask_i) - 1, lowest block first ----
-        uint32_t sbp = 0, ns = 0;
-#pragma unroll
-        for (int i = 0; i < RUN; i++) { sbp |= ns << (8 * i); ns += __popc((bmp >> (8 * i)) & 63u); }
-        {
-            int4* z = reinterpret_cast<int4*>(&sm.u.coef[0][0]);
-            for (uint32_t q = lane; q < ns * 16u; q += 32u) z[q] = make_int4(0, 0, 0, 0);
-        }
-        uint32_t st_i[RUN], n_i[RUN];
-#pragma unroll
-        for (int i = 0; i < RUN; i++) { st_i[i] = __shfl_sync(0xffffffffu, d.z, i) - jmin; n_i[i] = __shfl_sync(0xffffffffu, n_coef, i); }
-        __syncwarp();
-        // ---- dequantise into the pool (MD:3424-3429) ----
-        const uint32_t* __restrict__ qtab = J.hdr->qtab;
-        uint32_t m8 = 0;
-        for (uint32_t j0 = 0; j0 < ntot; j0 += 32u) {
-            const uint32_t j = j0 + (uint32_t)lane;
-            if (j < ntot) {
-                const uint32_t c = j0 == 0 ? ca : j0 == 32u ? cb : __ldg(cf + j);
-                int own = -1;
-#pragma unroll
-                for (int i = 0; i < RUN; i++) if (j - st_i[i] < n_i[i]) own = i;
-                if (own >= 0) {
-                    const int level = (int)(int16_t)(c & 0xFFFFu);
-                    const uint32_t pos = (c >> 16) & 63u, sub = (c >> 22) & 3u, blk = (c >> 24) & 7u, is8 = c >> 31;
-                    const uint32_t wq = __ldg(qtab + (is8 ? pos : 64u + (pos & 15u)));
-                    const uint32_t mask = (bmp >> (8 * own)) & 63u;
-                    const uint32_t slot = ((sbp >> (8 * own)) & 255u) + __popc(mask & ((1u << blk) - 1u));
-                    sm.u.coef[slot][is8 ? (wq & 63u) : sub * 16u + (wq & 15u)] = (int)(wq >> 8) * level;
-                    m8 |= is8 << (8 * own + blk);
-                }
-            }
-        }
-        m8 = __reduce_or_sync(0xffffffffu, m8);
-        if (lane < 6 * RUN) {
-            const uint32_t kk = (uint32_t)lane / 6u, b = (uint32_t)lane - 6u * kk;
-            const uint32_t mask = (bmp >> (8 * kk)) & 63u;
-            if ((mask >> b) & 1u) {
-                const uint32_t slot = ((sbp >> (8 * kk)) & 255u) + __popc(mask & ((1u << b) - 1u));
-                const uint32_t toff = kk * 384u + (b < 4u ? ((b >> 1) * 8u) * 16u + (b & 1u) * 8u : 256u + (b - 4u) * 64u);
-                sm.slotinfo[slot] = toff | (b < 4u ? 0u : 1u << 16) | ((m8 >> (8 * kk + b)) & 1u) << 17;
-            }
-        }
-        __syncwarp();
-
-        // ---- inverse transforms: eight lanes per pooled block (one row each), four blocks per pass ----
-        const int g = lane >> 3, r = lane & 7, i4 = r & 3, s0 = (r >> 2) * 2;
-        for (uint32_t base = 0; base < ns; base += 4u) {
-            const uint32_t slot = base + (uint32_t)g;
-            const bool has = slot < ns;
-            const uint32_t info = sm.slotinfo[has ? slot : 0u];
-            const bool is8 = (info >> 17) & 1u;
-            int32_t* B = sm.u.coef[has ? slot : 0u];
-            int32_t in[8], v[8];
-            if (has) {
-                const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r : s0 * 16 + 4 * i4));
-                const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r + 4 : (s0 + 1) * 16 + 4 * i4));
-                in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
-                if (is8) { if (r == 0) in[0] += 32; bfly8(in, v); }
-                else { if (i4 == 0) { in[0] += 32; in[4] += 32; } bfly4(in, v); bfly4(in + 4, v + 4); }
-            }
-            __syncwarp();
-            if (has) {
-                if (is8) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++) B[8 * q + r] = v[q];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; q++) { B[s0 * 16 + 4 * q + i4] = v[q]; B[(s0 + 1) * 16 + 4 * q + i4] = v[4 + q]; }
-                }
-            }
-            __syncwarp();
-            if (has) {
-                const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r : s0 * 16 + 4 * i4));
-                const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r + 4 : (s0 + 1) * 16 + 4 * i4));
-                in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
-                if (is8) bfly8(in, v); else { bfly4(in, v); bfly4(in + 4, v + 4); }
-                // either way the lane now holds the residuals of row r, columns 0..7 of its block: add onto the prediction
-                uint8_t* t = &sm.tile[0][0] + (info & 0xFFFFu) + r * ((info >> 16) & 1u ? 8 : 16);
-                uint2 px = *reinterpret_cast<uint2*>(t);
-                px.x = addsat4(px.x, v[0], v[1], v[2], v[3]);
-                px.y = addsat4(px.y, v[4], v[5], v[6], v[7]);
-                *reinterpret_cast<uint2*>(t) = px;
-            }
-            __syncwarp();
-        }
-    }
-
-    // ---- the tiles leave, lane-parallel over the run again: 16 luma bytes / 8 chroma bytes per lane and round ----
-    if (inter) {
-        const uint8_t* t = sm.tile[k];
-        uint8_t* const dy = J.dst + yoff;
-        uint8_t* const dc = J.dst + ysz + (yoff >> 1);
-#pragma unroll
-        for (int row = lane / RUN; row < 16; row += 32 / RUN)
-            *reinterpret_cast<uint4*>(dy + (row << LOG2S)) = *reinterpret_cast<const uint4*>(t + row * 16);
-#pragma unroll
-        for (int q = lane / RUN; q < 16; q += 32 / RUN)
-            *reinterpret_cast<uint2*>(dc + (q >> 3) * (S >> 1) + ((q & 7) << LOG2S)) = *reinterpret_cast<const uint2*>(t + 256 + q * 8);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // inter macroblocks, persistent chunk kernel: warps draw chunks of 16 consecutive macroblocks (four runs of four)
 // ------------------------------------------------------------------------------------------------
-// k_inter_run's CTAs live for about 1700 instructions per warp: CTA turnover and uneven warps inside a CTA leave a third of
-// the warp slots empty, and every run starts with two dependent trips to memory (job table, then descriptors).  Here the
-// grid is sized to the machine, warps draw chunks through an atomic ticket (the next ticket is requested before the
-// current chunk is worked on), lanes 0..15 decode the chunk's 16 descriptors at once, and the four runs of the chunk then
-// go through the same steps as in k_inter_run with their per-macroblock facts arriving by shuffle.
+// CTAs that live for one run (about 1700 instructions per warp) lose a third of the warp slots to CTA turnover and to
+// uneven warps inside a CTA, and every run starts with dependent trips to memory (job table, descriptors, leaves).  So
+// the grid is sized to the machine and warps draw chunks of 16 macroblocks through an atomic ticket (the next ticket is
+// requested before the current chunk is worked on).  Lanes 0..15 decode the chunk's 16 descriptors at once and fetch
+// leaves 0..3 of the split ones; the four runs of the chunk then go through the steps listed above with their
+// per-macroblock facts arriving by shuffle.
 constexpr int CH_WARPS = 4, CH_MBS = 16;
 
 // Window facts of one leaf as the prediction step wants them, 12 bits: column of the window inside its 16-byte-aligned
@@ -1508,27 +1268,10 @@ cudaError_t init_kernel_tables() {
     return cudaMemcpyToSymbol(c_blklist, lut, sizeof lut);
 }
 
-// MOBI_INTER_KERNEL selects the inter kernel: "chunk" = k_inter_chunk (persistent, tickets), "run4" / "run2" = k_inter_run with
-// 4 / 2 macroblocks per warp, "warp" = k_inter.
-static int inter_kernel_choice() {
-    static const int choice = [] {
-        const char* e = getenv("MOBI_INTER_KERNEL");
-        if (!e || !*e) return 0;
-        if (!strcmp(e, "chunk")) return 16;
-        if (!strcmp(e, "run4")) return 4;
-        if (!strcmp(e, "run2")) return 2;
-        return 0;
-    }();
-    return choice;
-}
-
-template <int RUN>
-static void launch_inter_run(const DevJob* jobs, int n_jobs, Geom g, uint32_t magic, const CUtensorMap& tm_l, const CUtensorMap& tm_c4, cudaStream_t st) {
-    const int per_cta = RUNK_WARPS * RUN;
-    dim3 grid((unsigned)((g.mbw * g.mbh + per_cta - 1) / per_cta), (unsigned)n_jobs);
-    if (g.log2S == 8) k_inter_run<8, RUN><<<grid, RUNK_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c4);
-    else if (g.log2S == 9) k_inter_run<9, RUN><<<grid, RUNK_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c4);
-    else k_inter_run<10, RUN><<<grid, RUNK_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c4);
+// k_inter_chunk unless MOBI_INTER_KERNEL=warp asks for k_inter (one warp per macroblock; kept for comparison).
+static bool inter_kernel_is_warp() {
+    static const bool warp = [] { const char* e = getenv("MOBI_INTER_KERNEL"); return e && !strcmp(e, "warp"); }();
+    return warp;
 }
 
 cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, const CUtensorMap& tm_c4,
@@ -1536,8 +1279,7 @@ cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorM
     *tickets_drawn = 0;
     if (n_jobs <= 0) return cudaSuccess;
     const uint32_t magic = (uint32_t)((0x100000000ull + (uint64_t)g.mbw - 1) / (uint64_t)g.mbw);
-    const int choice = inter_kernel_choice();
-    if (choice == 16) {
+    if (!inter_kernel_is_warp()) {
         const uint32_t cpp = (uint32_t)((g.mbw * g.mbh + CH_MBS - 1) / CH_MBS), n_chunks = cpp * (uint32_t)n_jobs;
         const uint32_t cpp_magic = (uint32_t)((0x100000000ull + (uint64_t)cpp - 1) / (uint64_t)cpp);
         uint32_t ctas = (uint32_t)sm_count * 7u;
@@ -1548,8 +1290,6 @@ cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorM
         *tickets_drawn = n_chunks + ctas * CH_WARPS;   // every warp draws exactly one ticket past the end
         return cudaGetLastError();
     }
-    if (choice == 4) { launch_inter_run<4>(jobs, n_jobs, g, magic, tm_l, tm_c4, st); return cudaGetLastError(); }
-    if (choice == 2) { launch_inter_run<2>(jobs, n_jobs, g, magic, tm_l, tm_c4, st); return cudaGetLastError(); }
     dim3 grid((unsigned)((g.mbw * g.mbh + INTER_WARPS - 1) / INTER_WARPS), (unsigned)n_jobs);
     if (g.log2S == 8) k_inter<8><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
     else if (g.log2S == 9) k_inter<9><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
