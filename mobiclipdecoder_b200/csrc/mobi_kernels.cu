@@ -840,12 +840,16 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
 // ------------------------------------------------------------------------------------------------
 // Per-warp shared state.  Pixel tiles: luma rows y-1..y+15, columns x-4..x+27 (column x at index 4, so x-1 = 3 and
 // the top-right / right-hand run x+16..x+20 = 20..24); chroma rows c-1..c+7, column c at index 4.
+// The residuals of ALL of a macroblock's transform units depend on its coefficient records only, so they are computed
+// before the macroblock waits for its neighbours (dequantise, transform, >> 6, all coded 8x8 blocks side by side like the
+// inter kernel does) and parked in resid[]; what remains on the wavefront's critical path per block is predict + add.
 struct IntraSmem {
-    uint8_t y[17][32];
-    uint8_t c[2][9][16];
-    int32_t coef[64];      // one transform block
+    union {
+        int32_t coef[6][64];   // coefficient blocks by 8x8 block id (0-3 luma raster, 4 U, 5 V); dead once resid[] is filled
+        struct { uint8_t y[17][32]; uint8_t c[2][9][16]; } t;   // the pixel tiles reuse the space
+    } u;
+    int16_t resid[384];    // residuals by pixel position (luma 16x16, U 8x8, V 8x8), saturated to 16 bits (exact under the final clip)
     uint32_t qtab[80];     // the picture's dequantisation words (MD:3897-3912)
-    uint32_t cf[384];      // the macroblock's coefficient records
 };
 
 // Is the 4-byte word at flat luma address `flat` (a) inside the array, (b) inside the visible picture, (c) part of a
@@ -956,6 +960,15 @@ __device__ __forceinline__ void intra_predict(uint8_t* t, int ts, int mode, int 
                                (uint32_t)plane_val<N>(t, ts, delta, x + 2, y) << 16 | (uint32_t)plane_val<N>(t, ts, delta, x + 3, y) << 24;
             *reinterpret_cast<uint32_t*>(t + y * ts + x) = w;
         }
+    } else if (N == 8) {
+        // directional predictors: every value is a byte (averages of bytes), so the pixels spread over all 32 lanes --
+        // two neighbours per lane, one 16-bit store -- instead of four per lane on half the warp: this sits on the
+        // wavefront's critical path
+        const int y = lane >> 2, x = (lane & 3) * 2;
+        const uint32_t w = (uint32_t)dir_px<N>(t, ts, mode, x, y) | (uint32_t)dir_px<N>(t, ts, mode, x + 1, y) << 8;
+        *reinterpret_cast<uint16_t*>(t + y * ts + x) = (uint16_t)w;
+    } else if (N == 4) {
+        if (lane < 16) { const int y = lane >> 2, x = lane & 3; t[y * ts + x] = (uint8_t)dir_px<N>(t, ts, mode, x, y); }
     } else {
         for (int i = lane; i < WORDS; i += 32) {
             const int y = i / WPR, x = (i % WPR) * 4;
@@ -967,47 +980,86 @@ __device__ __forceinline__ void intra_predict(uint8_t* t, int ts, int mode, int 
     __syncwarp();
 }
 
-// Residual of one transform unit added onto the tile (loc_116540 MD:2931 / sub_1166E8 MD:2958).  The unit's
-// coefficient records start at cf[cursor] and end at the record flagged "last".
-template <int N>
-__device__ __forceinline__ void intra_residual(uint8_t* t, int ts, int32_t* cb, const uint32_t* qtab, const uint32_t* cf,
-                                               uint32_t& cursor, uint32_t end, int lane) {
-    for (int i = lane; i < N * N; i += 32) cb[i] = 0;
+// Residuals of every transform unit of a macroblock (loc_116540 MD:2931 / sub_1166E8 MD:2958 / ReadDCTMatrix's
+// dequantisation MD:3424-3429): coefficient records carry their block / sub-block tags, so all of them are scattered
+// at once; eight lanes per coded 8x8 block (one row each, a block coded as four 4x4 units included), four blocks per pass.
+__device__ __forceinline__ void intra_residuals(IntraSmem& sm, const uint32_t* __restrict__ cf, int n_coef, uint32_t blkmask, int lane) {
+    {
+        int4* z = reinterpret_cast<int4*>(&sm.u.coef[0][0]);
+#pragma unroll
+        for (int i = 0; i < 3; i++) z[lane + 32 * i] = make_int4(0, 0, 0, 0);
+    }
     __syncwarp();
-    for (;;) {
-        const uint32_t j = cursor + lane;
-        const uint32_t c = j < end ? cf[j] : 0u;
-        const uint32_t lastmask = __ballot_sync(0xffffffffu, j < end && ((c >> 30) & 1u));
-        const int n = lastmask ? __ffs(lastmask) : 32;
-        if (lane < n && j < end) {
-            const uint32_t pos = (c >> 16) & 63u;
-            const uint32_t w = qtab[N == 8 ? pos : 64u + (pos & 15u)];
-            cb[w & (uint32_t)(N * N - 1)] = (int)(w >> 8) * (int)(int16_t)(c & 0xFFFFu);
+    uint32_t m8 = 0;
+    for (int j = lane; j < n_coef; j += 32) {
+        const uint32_t c = __ldg(cf + j);
+        const int level = (int)(int16_t)(c & 0xFFFFu);
+        const uint32_t pos = (c >> 16) & 63u, sub = (c >> 22) & 3u, blk = min((c >> 24) & 7u, 5u), is8 = c >> 31;
+        const uint32_t w = sm.qtab[is8 ? pos : 64u + (pos & 15u)];
+        sm.u.coef[blk][is8 ? (w & 63u) : sub * 16u + (w & 15u)] = (int)(w >> 8) * level;
+        m8 |= is8 << blk;
+    }
+    m8 = __reduce_or_sync(0xffffffffu, m8);
+    const uint32_t list = c_blklist[blkmask];   // ids of the coded blocks, one nibble each, lowest first
+    const int nblk = __popc(blkmask);
+    __syncwarp();
+    const int g = lane >> 3, r = lane & 7, i4 = r & 3, s0 = (r >> 2) * 2;
+    for (int base = 0; base < nblk; base += 4) {
+        const bool has = base + g < nblk;
+        const int b = (int)((list >> (4 * (base + g))) & 7u);
+        const bool is8 = (m8 >> b) & 1u;
+        int32_t* B = sm.u.coef[has ? b : 0];
+        int32_t in[8], v[8];
+        if (has) {
+            const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r : s0 * 16 + 4 * i4));
+            const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r + 4 : (s0 + 1) * 16 + 4 * i4));
+            in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
+            if (is8) { if (r == 0) in[0] += 32; bfly8(in, v); }
+            else { if (i4 == 0) { in[0] += 32; in[4] += 32; } bfly4(in, v); bfly4(in + 4, v + 4); }
         }
-        cursor += n;
-        if (lastmask || cursor >= end) break;
+        __syncwarp();
+        if (has) {
+            if (is8) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) B[8 * k + r] = v[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) { B[s0 * 16 + 4 * k + i4] = v[k]; B[(s0 + 1) * 16 + 4 * k + i4] = v[4 + k]; }
+            }
+        }
+        __syncwarp();
+        if (has) {
+            const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r : s0 * 16 + 4 * i4));
+            const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r + 4 : (s0 + 1) * 16 + 4 * i4));
+            in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
+            if (is8) bfly8(in, v); else { bfly4(in, v); bfly4(in + 4, v + 4); }
+            // either way the lane now holds row r, columns 0..7 of block b
+            uint4 o;
+            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(o.x) : "r"(v[1] >> 6), "r"(v[0] >> 6));
+            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(o.y) : "r"(v[3] >> 6), "r"(v[2] >> 6));
+            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(o.z) : "r"(v[5] >> 6), "r"(v[4] >> 6));
+            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(o.w) : "r"(v[7] >> 6), "r"(v[6] >> 6));
+            int16_t* rp = b < 4 ? sm.resid + ((b >> 1) * 8 + r) * 16 + (b & 1) * 8 : sm.resid + 256 + (b - 4) * 64 + r * 8;
+            *reinterpret_cast<uint4*>(rp) = o;
+        }
     }
     __syncwarp();
-    int32_t in[N], v[N];
-    if (lane < N) {
-#pragma unroll
-        for (int k = 0; k < N; k++) in[k] = cb[N * lane + k];
-        if (lane == 0) in[0] += 32;
-        if constexpr (N == 8) bfly8(in, v); else bfly4(in, v);
-    }
-    __syncwarp();
-    if (lane < N) {
-#pragma unroll
-        for (int k = 0; k < N; k++) cb[N * k + lane] = v[k];
-    }
-    __syncwarp();
-    if (lane < N) {
-#pragma unroll
-        for (int k = 0; k < N; k++) in[k] = cb[N * lane + k];
-        if constexpr (N == 8) bfly8(in, v); else bfly4(in, v);
-        uint32_t* row = reinterpret_cast<uint32_t*>(t + lane * ts);
-#pragma unroll
-        for (int k = 0; k < N; k += 4) row[k >> 2] = addclip4(row[k >> 2], v + k);
+}
+// Parked residuals of an NxN block added onto the tile (the "+ residual, clip" half of loc_116518 / loc_116628 MD:2898-2956).
+template <int N>
+__device__ __forceinline__ void add_resid(uint8_t* t, int ts, const int16_t* rp, int rpitch, int lane) {
+    constexpr int WORDS = N * N / 4, WPR = N / 4;
+    if (lane < WORDS) {
+        const int y = lane / WPR, x = (lane % WPR) * 4;
+        uint32_t* pw = reinterpret_cast<uint32_t*>(t + y * ts + x);
+        const uint2 rr = *reinterpret_cast<const uint2*>(rp + y * rpitch + x);
+        const uint32_t px = *pw;
+        const int p0 = (int)(px & 255u) + (int)(int16_t)(rr.x & 0xFFFFu), p1 = (int)((px >> 8) & 255u) + ((int)rr.x >> 16);
+        const int p2 = (int)((px >> 16) & 255u) + (int)(int16_t)(rr.y & 0xFFFFu), p3 = (int)(px >> 24) + ((int)rr.y >> 16);
+        uint32_t hi, out;
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(p3), "r"(p2), "r"(0));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(p1), "r"(p0), "r"(hi));
+        *pw = out;
     }
     __syncwarp();
 }
@@ -1019,19 +1071,20 @@ __device__ __forceinline__ IntraItem load_item(const IntraWork* w) {
     const uint2 w1 = __ldg(reinterpret_cast<const uint2*>(w) + 2);
     return IntraItem{w0.x, w0.y, w0.z, w0.w, w1.x, w1.y};
 }
-// Everything that does not depend on neighbouring macroblocks: the op list (returned, one op per lane), the
-// coefficient records and the picture's scale table into shared memory, zeroed tiles.
+// Everything that does not depend on neighbouring macroblocks: the op list (returned, one op per lane), the picture's
+// scale table, the residuals of all transform units, zeroed tiles.
 template <bool LOAD_QTAB>
 __device__ __forceinline__ uint32_t intra_prefetch(const DevJob& J, IntraSmem& sm, const IntraItem& it, int lane) {
     const int n_ops = (int)((it.info >> 2) & 127u), n_coef = (int)((it.info >> 9) & 511u);
+    const uint32_t blkmask = (it.info >> 18) & 63u;
     const uint32_t myop = lane < n_ops ? __ldg(J.ops + it.first_op + lane) : 0u;
-    const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs) + it.first_coef;
-    for (int i = lane; i < n_coef; i += 32) sm.cf[i] = __ldg(cf + i);
     if (LOAD_QTAB) {
         const uint32_t* qt = J.hdr->qtab;
         for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
     }
-    uint4* z = reinterpret_cast<uint4*>(&sm.y[0][0]);  // y and c tiles are contiguous: 832 B = 52 x 16
+    __syncwarp();   // the previous macroblock's tiles have been written out; the scale table is in place
+    if (n_coef && blkmask) intra_residuals(sm, reinterpret_cast<const uint32_t*>(J.coefs) + it.first_coef, n_coef, blkmask, lane);
+    uint4* z = reinterpret_cast<uint4*>(&sm.u.t.y[0][0]);  // y and c tiles are contiguous: 832 B = 52 x 16
     for (int i = lane; i < 52; i += 32) z[i] = make_uint4(0, 0, 0, 0);
     return myop;
 }
@@ -1050,16 +1103,16 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
     // slot i -> (destination word in the tiles, flat source address, plane); both of a lane's loads are issued before
     // either is stored, so the staging costs one L2 round trip
     auto slot = [&](int i, uint32_t*& dstw, int& flat, bool& chroma) {
-        if (i < 7) { dstw = reinterpret_cast<uint32_t*>(&sm.y[0][4 * i]); flat = yoff - S - 4 + 4 * i; chroma = false; }
-        else if (i < 23) { dstw = reinterpret_cast<uint32_t*>(&sm.y[i - 6][0]); flat = yoff + (i - 7) * S - 4; chroma = false; }
+        if (i < 7) { dstw = reinterpret_cast<uint32_t*>(&sm.u.t.y[0][4 * i]); flat = yoff - S - 4 + 4 * i; chroma = false; }
+        else if (i < 23) { dstw = reinterpret_cast<uint32_t*>(&sm.u.t.y[i - 6][0]); flat = yoff + (i - 7) * S - 4; chroma = false; }
         else if (i < 45) {
             const int k = i - 23, p = k >= 11 ? 1 : 0, q = k - 11 * p, base = coff + (p ? (S >> 1) : 0);
             chroma = true;
-            if (q < 3) { dstw = reinterpret_cast<uint32_t*>(&sm.c[p][0][4 * q]); flat = base - S - 4 + 4 * q; }
-            else { dstw = reinterpret_cast<uint32_t*>(&sm.c[p][q - 2][0]); flat = base + (q - 3) * S - 4; }
+            if (q < 3) { dstw = reinterpret_cast<uint32_t*>(&sm.u.t.c[p][0][4 * q]); flat = base - S - 4 + 4 * q; }
+            else { dstw = reinterpret_cast<uint32_t*>(&sm.u.t.c[p][q - 2][0]); flat = base + (q - 3) * S - 4; }
         } else {
             const int k = i - 45, r = k >> 1, h = k & 1;
-            dstw = reinterpret_cast<uint32_t*>(&sm.y[1 + r][20 + 4 * h]); flat = yoff + r * S + 16 + 4 * h; chroma = false;
+            dstw = reinterpret_cast<uint32_t*>(&sm.u.t.y[1 + r][20 + 4 * h]); flat = yoff + r * S + 16 + 4 * h; chroma = false;
         }
     };
     {
@@ -1079,32 +1132,34 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
     }
     __syncwarp();
 
-    uint32_t cursor = 0;
     for (int k = 0; k < n_ops; k++) {
         const uint32_t op = __shfl_sync(0xffffffffu, myop, k);
         const int mode = (int)(op & 31u), plane = (int)((op >> 6) & 3u), x4 = (int)((op >> 8) & 3u), y4 = (int)((op >> 10) & 3u);
         const bool res = (op >> 5) & 1u;
         const int delta = (int)(int16_t)(op >> 16);
-        uint8_t* tp; int ts, off;
-        if (plane == 0) { ts = 32; tp = &sm.y[1 + y4 * 4][4 + x4 * 4]; off = yoff + y4 * 4 * S + x4 * 4; }
-        else { ts = 16; tp = &sm.c[plane - 1][1 + y4 * 4][4 + x4 * 4]; off = coff + (plane == 2 ? (S >> 1) : 0) + y4 * 4 * S + x4 * 4; }
+        uint8_t* tp; const int16_t* rp; int ts, rs, off;
+        if (plane == 0) { ts = 32; rs = 16; tp = &sm.u.t.y[1 + y4 * 4][4 + x4 * 4]; rp = sm.resid + y4 * 4 * 16 + x4 * 4; off = yoff + y4 * 4 * S + x4 * 4; }
+        else {
+            ts = 16; rs = 8; tp = &sm.u.t.c[plane - 1][1 + y4 * 4][4 + x4 * 4]; rp = sm.resid + 256 + (plane - 1) * 64 + y4 * 4 * 8 + x4 * 4;
+            off = coff + (plane == 2 ? (S >> 1) : 0) + y4 * 4 * S + x4 * 4;
+        }
         const bool left_av = ((off - (plane == 2 ? (S >> 1) : 0)) & (S - 1)) != 0;  // MD:1923, VOffsetfix MD:1885
         const bool top_av = off >= S;                                               // MD:1924
         if (mode == 20) intra_predict<16>(tp, ts, 2, delta, left_av, top_av, lane);
         else if (mode >= 10) {
             if (mode != 19) intra_predict<4>(tp, ts, mode - 10, delta, left_av, top_av, lane);
-            if (res) intra_residual<4>(tp, ts, sm.coef, sm.qtab, sm.cf, cursor, (uint32_t)n_coef, lane);
+            if (res) add_resid<4>(tp, ts, rp, rs, lane);
         } else {
             if (mode != 9) intra_predict<8>(tp, ts, mode, delta, left_av, top_av, lane);
-            if (res) intra_residual<8>(tp, ts, sm.coef, sm.qtab, sm.cf, cursor, (uint32_t)n_coef, lane);
+            if (res) add_resid<8>(tp, ts, rp, rs, lane);
         }
     }
     // write the macroblock out
     const int lrow = lane >> 1, lhalf = lane & 1;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.y[1 + lrow][4 + lhalf * 8]);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.u.t.y[1 + lrow][4 + lhalf * 8]);
     *reinterpret_cast<uint2*>(J.dst + yoff + lrow * S + lhalf * 8) = make_uint2(src[0], src[1]);
     const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1;
-    const uint32_t cv = *reinterpret_cast<const uint32_t*>(&sm.c[cpl][1 + crow][4 + chalf * 4]);
+    const uint32_t cv = *reinterpret_cast<const uint32_t*>(&sm.u.t.c[cpl][1 + crow][4 + chalf * 4]);
     *reinterpret_cast<uint32_t*>(J.dst + (size_t)S * g.H + coff + (cpl ? (S >> 1) : 0) + crow * S + chalf * 4) = cv;
 }
 
@@ -1169,8 +1224,12 @@ __global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __re
         for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
     }
     for (int row = warp; row < g.mbh; row += KEY_WARPS) {
+        IntraItem it_next = load_item(items + row * mbw);
         for (int x = 0; x < mbw; x++) {
-            const IntraItem it = load_item(items + row * mbw + x);
+            // the next macroblock's work item travels one iteration ahead, and its ops and coefficient records are pulled
+            // into L1 while this one is reconstructed: two dependent trips to memory less on the wavefront's critical path
+            const IntraItem it = it_next;
+            if (x + 1 < mbw) it_next = load_item(items + row * mbw + x + 1);
             const uint32_t myop = intra_prefetch<false>(J, sm, it, lane);
             if (lane == 0 && row > 0 && it.wait) {
                 // neighbours by raster index (SURVEY.md 8a hazard 2): left of column 0 = last macroblock of the row above
@@ -1186,6 +1245,12 @@ __global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __re
                 __threadfence_block();   // the producer fenced at gpu scope before moving its counter; the pixel loads below bypass L1
             }
             __syncwarp();
+            if (x + 1 < mbw) {
+                const uint8_t* c1 = reinterpret_cast<const uint8_t*>(J.coefs + it_next.first_coef);
+                const uint32_t bytes = ((it_next.info >> 9) & 511u) * 4u + (uint32_t)(reinterpret_cast<uintptr_t>(c1) & 127u);
+                if ((uint32_t)lane * 128u < bytes) asm volatile("prefetch.global.L1 [%0];" :: "l"(c1 + lane * 128));
+                if (lane == 31) asm volatile("prefetch.global.L1 [%0];" :: "l"(J.ops + it_next.first_op));
+            }
             intra_reconstruct(J, g, sm, it, myop, lane);
             __syncwarp();
             if (lane == 0) {
