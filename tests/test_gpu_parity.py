@@ -261,3 +261,62 @@ def test_config5_eight_streams_lockstep():
             for s in range(n_streams):
                 assert np.array_equal(got[s], oracles[s].i420()), 'stream %d frame %d' % (s, f)
     b.close()
+
+
+def test_submit_packed_leaf_order_is_free():
+    """A macroblock split once carries two leaf records; the parser emits top/left first, but the packed-array contract
+    (include/mobicuda.h) does not fix the order.  Swapping the two records of every such macroblock must not change a
+    single pixel (the inter kernel fetches both leaves as boxes and picks by position, not by record index)."""
+    import ctypes as C
+    name = 'moflex_400x240'
+    w, h, ver, _ = CONFIGS[name]
+    fr = frames(name, 31, 5)
+    dec, par, ora = MobiclipDecoder(w, h, ver), MobiParser(w, h, ver), Oracle(w, h, ver)
+    swapped = 0
+    for data, key in fr:
+        rc, off, pf = par.parse(data, 0)
+        assert rc == 0
+        hdr = pf.hdr.contents
+        for m in range(hdr.n_mb):
+            mb = pf.mbs[m]
+            if (mb.info & 3) == 0 and ((mb.info >> 2) & 127) == 2:
+                a, b = pf.parts[mb.first_sub], pf.parts[mb.first_sub + 1]
+                ta = (a.xy, a.shape, a.mvx, a.mvy)
+                a.xy, a.shape, a.mvx, a.mvy = b.xy, b.shape, b.mvx, b.mvy
+                b.xy, b.shape, b.mvx, b.mvy = ta
+                swapped += 1
+        dec.SubmitPacked(pf)
+        assert ora.decode(data, 0, False)[0]
+        assert np.array_equal(dec.Y[0], ora.y), _diff_report(dec.Y[0].ravel(), ora.y.ravel(), 512)
+        assert np.array_equal(dec.UV[0], ora.uv)
+    assert swapped > 50
+    dec.close()
+
+
+def test_per_macroblock_inter_kernel_agrees():
+    """MOBI_INTER_KERNEL=warp selects the one-warp-per-macroblock kernel (kept for comparison); it is read once per
+    process, so the check runs in a child process and compares a digest of every decoded plane with this process's."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import hashlib, sys\n"
+        "from mobiclipdecoder_b200 import MobiclipDecoder\n"
+        "from mobiclipdecoder_b200.workloads import CONFIGS, frames\n"
+        "w, h, ver, _ = CONFIGS['moc5_640x480']\n"
+        "dec = MobiclipDecoder(w, h, ver)\n"
+        "d = hashlib.sha256()\n"
+        "for data, key in frames('moc5_640x480', 9, 12):\n"
+        "    dec.Data, dec.Offset = data, 0\n"
+        "    assert dec.DecodeFrame(False) is not None\n"
+        "    d.update(dec.Y[0].tobytes()); d.update(dec.UV[0].tobytes())\n"
+        "print(d.hexdigest())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for kern in ('warp', 'chunk'):
+        env = dict(os.environ, MOBI_INTER_KERNEL=kern, PYTHONPATH=root + os.pathsep + os.environ.get('PYTHONPATH', ''))
+        r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[kern] = r.stdout.strip().splitlines()[-1]
+    assert out['warp'] == out['chunk']
