@@ -996,7 +996,7 @@ __device__ __forceinline__ void intra_residuals(IntraSmem& sm, const uint32_t* _
         const int level = (int)(int16_t)(c & 0xFFFFu);
         const uint32_t pos = (c >> 16) & 63u, sub = (c >> 22) & 3u, blk = min((c >> 24) & 7u, 5u), is8 = c >> 31;
         const uint32_t w = sm.qtab[is8 ? pos : 64u + (pos & 15u)];
-        sm.u.coef[blk][is8 ? (w & 63u) : sub * 16u + (w & 15u)] = (int)(w >> 8) * level;
+        if ((blkmask >> blk) & 1u) sm.u.coef[blk][is8 ? (w & 63u) : sub * 16u + (w & 15u)] = (int)(w >> 8) * level;   // (the caller may ask for luma or chroma only)
         m8 |= is8 << blk;
     }
     m8 = __reduce_or_sync(0xffffffffu, m8);
@@ -1073,10 +1073,12 @@ __device__ __forceinline__ IntraItem load_item(const IntraWork* w) {
 }
 // Everything that does not depend on neighbouring macroblocks: the op list (returned, one op per lane), the picture's
 // scale table, the residuals of all transform units, zeroed tiles.
+// PLANES: 1 = luma only, 2 = chroma only, 3 = the whole macroblock (the I-picture kernel runs a luma and a chroma
+// wavefront side by side: neither plane's predictors ever read the other plane).
 template <bool LOAD_QTAB>
-__device__ __forceinline__ uint32_t intra_prefetch(const DevJob& J, IntraSmem& sm, const IntraItem& it, int lane) {
+__device__ __forceinline__ uint32_t intra_prefetch(const DevJob& J, IntraSmem& sm, const IntraItem& it, int lane, const int PLANES) {
     const int n_ops = (int)((it.info >> 2) & 127u), n_coef = (int)((it.info >> 9) & 511u);
-    const uint32_t blkmask = (it.info >> 18) & 63u;
+    const uint32_t blkmask = ((it.info >> 18) & 63u) & (PLANES == 1 ? 0x0Fu : PLANES == 2 ? 0x30u : 0x3Fu);
     const uint32_t myop = lane < n_ops ? __ldg(J.ops + it.first_op + lane) : 0u;
     if (LOAD_QTAB) {
         const uint32_t* qt = J.hdr->qtab;
@@ -1089,7 +1091,7 @@ __device__ __forceinline__ uint32_t intra_prefetch(const DevJob& J, IntraSmem& s
     return myop;
 }
 // Stage the neighbourhood, run the ops in stream order on the tiles, write the macroblock out.
-__device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g, IntraSmem& sm, const IntraItem& it, uint32_t myop, int lane) {
+__device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g, IntraSmem& sm, const IntraItem& it, uint32_t myop, int lane, const int PLANES) {
     const int S = g.S;
     const uint32_t m = it.m;
     const int n_ops = (int)((it.info >> 2) & 127u), n_coef = (int)((it.info >> 9) & 511u);
@@ -1121,11 +1123,12 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
         slot(lane, d0, f0, c0);
         const bool two = lane + 32 < n;
         slot(two ? lane + 32 : lane, d1, f1, c1);
-        const uint32_t v0 = c0 ? nb_chroma4(J, g, f0, m) : nb_luma4(J, g, f0, m);
-        const uint32_t v1 = two ? (c1 ? nb_chroma4(J, g, f1, m) : nb_luma4(J, g, f1, m)) : 0u;
-        *d0 = v0;
-        if (two) *d1 = v1;
-        if (lane + 64 < n) {   // only in the wrap case
+        const bool w0 = PLANES == 3 || c0 == (PLANES == 2), w1 = two && (PLANES == 3 || c1 == (PLANES == 2));   // this plane group's slots only
+        const uint32_t v0 = !w0 ? 0u : c0 ? nb_chroma4(J, g, f0, m) : nb_luma4(J, g, f0, m);
+        const uint32_t v1 = !w1 ? 0u : c1 ? nb_chroma4(J, g, f1, m) : nb_luma4(J, g, f1, m);
+        if (w0) *d0 = v0;
+        if (w1) *d1 = v1;
+        if ((PLANES & 1) && lane + 64 < n) {   // only in the wrap case (luma)
             slot(lane + 64, d0, f0, c0);
             *d0 = nb_luma4(J, g, f0, m);
         }
@@ -1135,6 +1138,7 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
     for (int k = 0; k < n_ops; k++) {
         const uint32_t op = __shfl_sync(0xffffffffu, myop, k);
         const int mode = (int)(op & 31u), plane = (int)((op >> 6) & 3u), x4 = (int)((op >> 8) & 3u), y4 = (int)((op >> 10) & 3u);
+        if (PLANES != 3 && (plane == 0) != (PLANES == 1)) continue;   // the other wavefront's op
         const bool res = (op >> 5) & 1u;
         const int delta = (int)(int16_t)(op >> 16);
         uint8_t* tp; const int16_t* rp; int ts, rs, off;
@@ -1155,12 +1159,16 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
         }
     }
     // write the macroblock out
-    const int lrow = lane >> 1, lhalf = lane & 1;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.u.t.y[1 + lrow][4 + lhalf * 8]);
-    *reinterpret_cast<uint2*>(J.dst + yoff + lrow * S + lhalf * 8) = make_uint2(src[0], src[1]);
-    const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1;
-    const uint32_t cv = *reinterpret_cast<const uint32_t*>(&sm.u.t.c[cpl][1 + crow][4 + chalf * 4]);
-    *reinterpret_cast<uint32_t*>(J.dst + (size_t)S * g.H + coff + (cpl ? (S >> 1) : 0) + crow * S + chalf * 4) = cv;
+    if (PLANES & 1) {
+        const int lrow = lane >> 1, lhalf = lane & 1;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.u.t.y[1 + lrow][4 + lhalf * 8]);
+        *reinterpret_cast<uint2*>(J.dst + yoff + lrow * S + lhalf * 8) = make_uint2(src[0], src[1]);
+    }
+    if (PLANES & 2) {
+        const int cpl = lane >> 4, crow = (lane >> 1) & 7, chalf = lane & 1;
+        const uint32_t cv = *reinterpret_cast<const uint32_t*>(&sm.u.t.c[cpl][1 + crow][4 + chalf * 4]);
+        *reinterpret_cast<uint32_t*>(J.dst + (size_t)S * g.H + coff + (cpl ? (S >> 1) : 0) + crow * S + chalf * 4) = cv;
+    }
 }
 
 // Scattered intra macroblocks (those inside P-pictures): persistent warps draw tickets from a dependency-depth-ordered
@@ -1177,7 +1185,7 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 8) k_intra(const DevJob* __r
         if (t >= n_work) break;
         const IntraItem it = load_item(work + t);
         const DevJob& J = jobs[it.job];
-        const uint32_t myop = intra_prefetch<true>(J, sm, it, lane);
+        const uint32_t myop = intra_prefetch<true>(J, sm, it, lane, 3);
         // wait for the intra neighbours whose pixels this macroblock's predictors read (host-computed mask)
         if (lane < 4 && ((it.wait >> lane) & 1u)) {
             const int nb = lane == 0 ? (int)it.m - 1 : (int)it.m - g.mbw - 2 + lane;
@@ -1191,7 +1199,7 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 8) k_intra(const DevJob* __r
             }
         }
         __syncwarp();
-        intra_reconstruct(J, g, sm, it, myop, lane);
+        intra_reconstruct(J, g, sm, it, myop, lane, 3);
         // release: every lane's pixel stores happen-before the stamp (bar.warp.sync orders the lanes' stores before
         // lane 0's release at gpu scope through cumulativity)
         __syncwarp();
@@ -1199,38 +1207,28 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 8) k_intra(const DevJob* __r
     }
 }
 
-// I-pictures: one CTA per picture, one warp per macroblock row (warp w takes rows w, w + KEY_WARPS, ...), macroblocks of
-// a row left to right.  The left neighbour is the warp's own previous macroblock; the rows above are awaited through
-// per-row progress counters in shared memory, so the wavefront's per-level latency is the macroblock's own work plus one
-// L2 round trip for the neighbour pixels -- no flag traffic through L2.  All rows of a picture live in one CTA, so every
-// awaited row is resident: no deadlock.
-constexpr int KEY_WARPS = 16;
+// I-pictures: one CTA per picture, TWO warps per macroblock row -- one walks the row's luma, the other its chroma (no
+// predictor reads across planes, so they are independent wavefronts and the per-macroblock chain of dependent steps
+// shrinks to the longer of the two) -- macroblocks of a row left to right, rows r, r + KEY_ROWS, ... per warp pair.  The
+// left neighbour is the warp's own previous macroblock; the rows above are awaited through per-row, per-plane-group
+// progress counters in shared memory, so the wavefront's per-level latency is the macroblock's own work plus one L2 round
+// trip for the neighbour pixels -- no flag traffic through L2.  All rows of a picture live in one CTA, so every awaited
+// row is resident: no deadlock.
+constexpr int KEY_ROWS = 16, KEY_WARPS = 2 * KEY_ROWS;
 struct KeyPic { uint32_t job, work_base; };
-__global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __restrict__ jobs, const IntraWork* __restrict__ work,
-                                                              const KeyPic* __restrict__ pics, Geom g, uint32_t* resident) {
-    __shared__ __align__(16) IntraSmem s_all[KEY_WARPS];
-    __shared__ uint32_t s_prog[64];   // macroblocks finished per macroblock row (H <= 1024); accessed with atomics only
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) atomicAdd(resident, 1u);   // this CTA holds its SM resources now (see k_gate)
-    if (threadIdx.x < 64) s_prog[threadIdx.x] = 0;
-    __syncthreads();
-    IntraSmem& sm = s_all[warp];
-    const KeyPic pic = pics[blockIdx.x];
-    const DevJob& J = jobs[pic.job];
-    const IntraWork* items = work + pic.work_base;   // raster order: every macroblock of an I-picture is intra
+
+// PLANES is a run-time value here on purpose: one copy of the (large) intra code serves both wavefronts, and the
+// instruction cache is what a handful of latency-bound warps live on.
+__device__ __forceinline__ void key_rows(const DevJob& J, const IntraWork* __restrict__ items, const Geom& g, IntraSmem& sm, uint32_t* prog, int first_row, int lane, const int PLANES) {
     const int mbw = g.mbw;
-    if (warp < g.mbh) {   // the picture's scale table: once per warp, not once per macroblock
-        const uint32_t* qt = J.hdr->qtab;
-        for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
-    }
-    for (int row = warp; row < g.mbh; row += KEY_WARPS) {
+    for (int row = first_row; row < g.mbh; row += KEY_ROWS) {
         IntraItem it_next = load_item(items + row * mbw);
         for (int x = 0; x < mbw; x++) {
             // the next macroblock's work item travels one iteration ahead, and its ops and coefficient records are pulled
             // into L1 while this one is reconstructed: two dependent trips to memory less on the wavefront's critical path
             const IntraItem it = it_next;
             if (x + 1 < mbw) it_next = load_item(items + row * mbw + x + 1);
-            const uint32_t myop = intra_prefetch<false>(J, sm, it, lane);
+            const uint32_t myop = intra_prefetch<false>(J, sm, it, lane, PLANES);
             if (lane == 0 && row > 0 && it.wait) {
                 // neighbours by raster index (SURVEY.md 8a hazard 2): left of column 0 = last macroblock of the row above
                 // (bit 0), top-left of column 0 = last macroblock two rows up (bit 1); top-right of the last column is
@@ -1240,8 +1238,8 @@ __global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __re
                 if (it.wait & 2u) { if (x == 0) need2 = (uint32_t)mbw; else need1 = max(need1, (uint32_t)x); }
                 if (it.wait & 4u) need1 = max(need1, (uint32_t)x + 1u);
                 if ((it.wait & 8u) && x + 1 < mbw) need1 = max(need1, (uint32_t)x + 2u);
-                while (atomicAdd(&s_prog[row - 1], 0u) < need1) __nanosleep(20);
-                if (need2 && row > 1) while (atomicAdd(&s_prog[row - 2], 0u) < need2) __nanosleep(20);
+                while (atomicAdd(&prog[row - 1], 0u) < need1) __nanosleep(20);
+                if (need2 && row > 1) while (atomicAdd(&prog[row - 2], 0u) < need2) __nanosleep(20);
                 __threadfence_block();   // the producer fenced at gpu scope before moving its counter; the pixel loads below bypass L1
             }
             __syncwarp();
@@ -1251,14 +1249,34 @@ __global__ void __launch_bounds__(KEY_WARPS * 32) k_intra_key(const DevJob* __re
                 if ((uint32_t)lane * 128u < bytes) asm volatile("prefetch.global.L1 [%0];" :: "l"(c1 + lane * 128));
                 if (lane == 31) asm volatile("prefetch.global.L1 [%0];" :: "l"(J.ops + it_next.first_op));
             }
-            intra_reconstruct(J, g, sm, it, myop, lane);
+            intra_reconstruct(J, g, sm, it, myop, lane, PLANES);
             __syncwarp();
             if (lane == 0) {
                 __threadfence();            // the row's pixels are in L2 before the counter moves
-                atomicExch(&s_prog[row], (uint32_t)x + 1u);
+                atomicExch(&prog[row], (uint32_t)x + 1u);
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(KEY_WARPS * 32, 1) k_intra_key(const DevJob* __restrict__ jobs, const IntraWork* __restrict__ work,
+                                                                 const KeyPic* __restrict__ pics, Geom g, uint32_t* resident) {
+    extern __shared__ __align__(16) uint8_t s_key_raw[];   // KEY_WARPS x IntraSmem: above the 48 KB static limit
+    IntraSmem* s_all = reinterpret_cast<IntraSmem*>(s_key_raw);
+    __shared__ uint32_t s_prog[2][64];   // macroblocks finished per macroblock row (H <= 1024), luma / chroma; accessed with atomics only
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) atomicAdd(resident, 1u);   // this CTA holds its SM resources now (see k_gate)
+    if (threadIdx.x < 128) s_prog[threadIdx.x >> 6][threadIdx.x & 63] = 0;
+    __syncthreads();
+    IntraSmem& sm = s_all[warp];
+    const KeyPic pic = pics[blockIdx.x];
+    const DevJob& J = jobs[pic.job];
+    const IntraWork* items = work + pic.work_base;   // raster order: every macroblock of an I-picture is intra
+    if ((warp >> 1) < g.mbh) {   // the picture's scale table: once per warp, not once per macroblock
+        const uint32_t* qt = J.hdr->qtab;
+        for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
+    }
+    key_rows(J, items, g, sm, s_prog[warp & 1], warp >> 1, lane, 1 + (warp & 1));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1379,7 +1397,10 @@ cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_w
 
 cudaError_t launch_intra_key(const DevJob* jobs, const IntraWork* work, const void* pics, int n_pics, Geom g, uint32_t* resident, cudaStream_t st) {
     if (n_pics <= 0) return cudaSuccess;
-    k_intra_key<<<(unsigned)n_pics, KEY_WARPS * 32, 0, st>>>(jobs, work, reinterpret_cast<const KeyPic*>(pics), g, resident);
+    // per device, so set on every launch (a host-side table lookup)
+    const cudaError_t attr = cudaFuncSetAttribute(k_intra_key, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KEY_WARPS * sizeof(IntraSmem)));
+    if (attr != cudaSuccess) return attr;
+    k_intra_key<<<(unsigned)n_pics, KEY_WARPS * 32, KEY_WARPS * sizeof(IntraSmem), st>>>(jobs, work, reinterpret_cast<const KeyPic*>(pics), g, resident);
     return cudaGetLastError();
 }
 
