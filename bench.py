@@ -275,6 +275,8 @@ def main():
     torch.cuda.synchronize()
     sharding.barrier(dist if world > 1 else None, local_rank)
     ms_local = e0.elapsed_time(e1)
+    if os.environ.get('MOBI_BENCH_DEBUG'):
+        sys.stderr.write('rank %d: value leg %.4f ms for %d steps\n' % (rank, ms_local, K))
     st1 = batch.stats()
     ms = sharding.max_over_ranks(dist if world > 1 else None, ms_local, torch, dev)
     d = {k: st1[k] - st0[k] for k in st1}
