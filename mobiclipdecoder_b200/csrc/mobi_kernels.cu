@@ -475,10 +475,11 @@ struct RunSmem {
         uint8_t raw[REGION];
         int32_t coef[SLOTS][64];
     } u;
-    uint8_t tile[RUN][384];     // prediction (+ residual): luma 16 rows x 16, then U 8x8, V 8x8
+    static constexpr int TILE = 416;   // 384 used; 416 keeps the four tiles 32 bytes apart modulo 128: the run-parallel 16-byte reads of the final store hit distinct banks
+    uint8_t tile[RUN][TILE];    // prediction (+ residual): luma 16 rows x 16, then U 8x8, V 8x8
     uint32_t slotinfo[SLOTS];   // per pooled block: byte offset of its pixels in tile[][] | chroma << 16 | 8x8 transform << 17
     uint64_t bar[RUN];
-    uint8_t pad[(128 - (REGION + RUN * 384 + SLOTS * 4 + RUN * 8) % 128) % 128];
+    uint8_t pad[(128 - (REGION + RUN * TILE + SLOTS * 4 + RUN * 8) % 128) % 128];
 };
 static_assert(sizeof(RunSmem<4>) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 static_assert(sizeof(RunSmem<4>) * 4 + 1024 <= 233472 / 7, "seven 4-warp CTAs per SM");
@@ -509,6 +510,14 @@ __device__ __forceinline__ uint32_t tile_row4_p64(const uint8_t* base, uint32_t 
 // leaves 0..3 of the split ones; the four runs of the chunk then go through the steps listed above with their
 // per-macroblock facts arriving by shuffle.
 constexpr int CH_WARPS = 4, CH_MBS = 16;
+
+// Word index of element (row, col) of a pooled 8x8 coefficient block.  Plain row-major puts rows r and r+4 of a block,
+// and the same row of the four blocks of a pass, on the same banks (16-byte row loads 2-way, transposed stores 4-way
+// conflicted: ncu source counters).  Rows 4-7 swap their 16-byte halves, and the low two row bits are XORed with the
+// block's slot: row loads, transposed stores and the scatter then spread over all banks.  Every access goes through here.
+__device__ __forceinline__ uint32_t pool_word(uint32_t slot, uint32_t row, uint32_t col) {
+    return ((row ^ (slot & 3u)) << 3) | (col ^ ((row & 4u)));
+}
 
 // Window facts of one leaf as the prediction step wants them, 12 bits: column of the window inside its 16-byte-aligned
 // box (4), luma half-pel phase (2), the same for the chroma window (4 + 2).
@@ -755,7 +764,8 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
                                 const uint32_t wq = __ldg(qtab + (is8 ? pos : 64u + (pos & 15u)));
                                 const uint32_t mask = (bmp >> (8 * own)) & 63u;
                                 const uint32_t slot = ((sbp >> (8 * own)) & 255u) + __popc(mask & ((1u << blk) - 1u));
-                                sm.u.coef[slot][is8 ? (wq & 63u) : sub * 16u + (wq & 15u)] = (int)(wq >> 8) * level;
+                                const uint32_t e = is8 ? (wq & 63u) : sub * 16u + (wq & 15u);
+                                sm.u.coef[slot][pool_word(slot, e >> 3, e & 7u)] = (int)(wq >> 8) * level;
                                 m8 |= is8 << (8 * own + blk);
                             }
                         }
@@ -766,7 +776,7 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
                         const uint32_t mask = (bmp >> (8 * kk)) & 63u;
                         if ((mask >> b) & 1u) {
                             const uint32_t slot = ((sbp >> (8 * kk)) & 255u) + __popc(mask & ((1u << b) - 1u));
-                            const uint32_t toff = kk * 384u + (b < 4u ? ((b >> 1) * 8u) * 16u + (b & 1u) * 8u : 256u + (b - 4u) * 64u);
+                            const uint32_t toff = kk * (uint32_t)Smem::TILE + (b < 4u ? ((b >> 1) * 8u) * 16u + (b & 1u) * 8u : 256u + (b - 4u) * 64u);
                             sm.slotinfo[slot] = toff | (b < 4u ? 0u : 1u << 16) | ((m8 >> (8 * kk + b)) & 1u) << 17;
                         }
                     }
@@ -780,10 +790,15 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
                         const uint32_t info = sm.slotinfo[has ? slot : 0u];
                         const bool is8 = (info >> 17) & 1u;
                         int32_t* B = sm.u.coef[has ? slot : 0u];
+                        // this lane's two 4-word groups: row rr of an 8x8 block, or row i4 of 4x4 units s0 and s0+1 (elements
+                        // s0*16 + 4*i4 .. and (s0+1)*16 + 4*i4 ..: block rows 2*s0 + (i4>>1) and 2*s0 + 2 + (i4>>1), columns 4*(i4&1) ..)
+                        const uint32_t rlo = is8 ? (uint32_t)rr : (uint32_t)(2 * s0 + (i4 >> 1)), rhi = is8 ? (uint32_t)rr : rlo + 2u;
+                        const uint32_t clo = is8 ? 0u : (uint32_t)(4 * (i4 & 1)), chi = is8 ? 4u : clo;
+                        const uint32_t wlo = pool_word(slot, rlo, clo), whi = pool_word(slot, rhi, chi);
                         int32_t in[8], v[8];
                         if (has) {
-                            const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * rr : s0 * 16 + 4 * i4));
-                            const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * rr + 4 : (s0 + 1) * 16 + 4 * i4));
+                            const int4 lo = *reinterpret_cast<const int4*>(B + wlo);
+                            const int4 hi = *reinterpret_cast<const int4*>(B + whi);
                             in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
                             if (is8) { if (rr == 0) in[0] += 32; bfly8(in, v); }
                             else { if (i4 == 0) { in[0] += 32; in[4] += 32; } bfly4(in, v); bfly4(in + 4, v + 4); }
@@ -792,16 +807,20 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
                         if (has) {
                             if (is8) {
 #pragma unroll
-                                for (int q = 0; q < 8; q++) B[8 * q + rr] = v[q];
+                                for (int q = 0; q < 8; q++) B[pool_word(slot, (uint32_t)q, (uint32_t)rr)] = v[q];   // element 8*q + rr
                             } else {
 #pragma unroll
-                                for (int q = 0; q < 4; q++) { B[s0 * 16 + 4 * q + i4] = v[q]; B[(s0 + 1) * 16 + 4 * q + i4] = v[4 + q]; }
+                                for (int q = 0; q < 4; q++) {   // elements s0*16 + 4*q + i4 and (s0+1)*16 + 4*q + i4
+                                    const uint32_t e0 = (uint32_t)(s0 * 16 + 4 * q + i4);
+                                    B[pool_word(slot, e0 >> 3, e0 & 7u)] = v[q];
+                                    B[pool_word(slot, (e0 >> 3) + 2u, e0 & 7u)] = v[4 + q];
+                                }
                             }
                         }
                         __syncwarp();
                         if (has) {
-                            const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * rr : s0 * 16 + 4 * i4));
-                            const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * rr + 4 : (s0 + 1) * 16 + 4 * i4));
+                            const int4 lo = *reinterpret_cast<const int4*>(B + wlo);
+                            const int4 hi = *reinterpret_cast<const int4*>(B + whi);
                             in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
                             if (is8) bfly8(in, v); else { bfly4(in, v); bfly4(in + 4, v + 4); }
                             // either way the lane now holds the residuals of row rr, columns 0..7 of its block: add onto the prediction
