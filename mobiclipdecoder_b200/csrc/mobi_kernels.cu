@@ -477,7 +477,7 @@ struct RunSmem {
     } u;
     static constexpr int TILE = 416;   // 384 used; 416 keeps the four tiles 32 bytes apart modulo 128: the run-parallel 16-byte reads of the final store hit distinct banks
     uint8_t tile[RUN][TILE];    // prediction (+ residual): luma 16 rows x 16, then U 8x8, V 8x8
-    uint32_t slotinfo[SLOTS];   // per pooled block: byte offset of its pixels in tile[][] | chroma << 16 | 8x8 transform << 17
+    uint32_t slotinfo[SLOTS];   // per pooled block, in the order the passes visit them: byte offset of its pixels in tile[][] | chroma << 16 | 8x8 transform << 17 | pool slot << 18
     uint64_t bar[RUN];
     uint8_t pad[(128 - (REGION + RUN * TILE + SLOTS * 4 + RUN * 8) % 128) % 128];
 };
@@ -771,13 +771,22 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
                         }
                     }
                     m8 = __reduce_or_sync(0xffffffffu, m8);
-                    if (lane < 6 * RUN) {
+                    {
+                        // One lane per (macroblock, block) of the run.  The passes visit the blocks transformed as one 8x8 first and
+                        // the ones transformed as four 4x4 after them, so that a pass rarely has to run both butterflies (60 % / 40 %
+                        // on the bench mix: unsorted, five passes in six are mixed); slotinfo[] is indexed by that visiting position
+                        // and carries the pool slot.
                         const uint32_t kk = (uint32_t)lane / 6u, b = (uint32_t)lane - 6u * kk;
-                        const uint32_t mask = (bmp >> (8 * kk)) & 63u;
-                        if ((mask >> b) & 1u) {
+                        const uint32_t mask = lane < 6 * RUN ? (bmp >> (8 * kk)) & 63u : 0u;
+                        const bool coded = (mask >> b) & 1u;
+                        const bool t8 = coded && ((m8 >> (8 * kk + b)) & 1u);
+                        const uint32_t cm = __ballot_sync(0xffffffffu, coded), m8b = __ballot_sync(0xffffffffu, t8);
+                        if (coded) {
+                            const uint32_t lt = (1u << lane) - 1u;
+                            const uint32_t pos = t8 ? __popc(m8b & lt) : __popc(m8b) + __popc(cm & ~m8b & lt);
                             const uint32_t slot = ((sbp >> (8 * kk)) & 255u) + __popc(mask & ((1u << b) - 1u));
                             const uint32_t toff = kk * (uint32_t)Smem::TILE + (b < 4u ? ((b >> 1) * 8u) * 16u + (b & 1u) * 8u : 256u + (b - 4u) * 64u);
-                            sm.slotinfo[slot] = toff | (b < 4u ? 0u : 1u << 16) | ((m8 >> (8 * kk + b)) & 1u) << 17;
+                            sm.slotinfo[pos] = toff | (b < 4u ? 0u : 1u << 16) | (t8 ? 1u << 17 : 0u) | slot << 18;
                         }
                     }
                     __syncwarp();
@@ -785,11 +794,11 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
                     // ---- inverse transforms: eight lanes per pooled block (one row each), four blocks per pass ----
                     const int g = lane >> 3, rr = lane & 7, i4 = rr & 3, s0 = (rr >> 2) * 2;
                     for (uint32_t base = 0; base < ns; base += 4u) {
-                        const uint32_t slot = base + (uint32_t)g;
-                        const bool has = slot < ns;
-                        const uint32_t info = sm.slotinfo[has ? slot : 0u];
+                        const bool has = base + (uint32_t)g < ns;
+                        const uint32_t info = sm.slotinfo[has ? base + (uint32_t)g : 0u];
                         const bool is8 = (info >> 17) & 1u;
-                        int32_t* B = sm.u.coef[has ? slot : 0u];
+                        const uint32_t slot = (info >> 18) & 31u;
+                        int32_t* B = sm.u.coef[slot];
                         // this lane's two 4-word groups: row rr of an 8x8 block, or row i4 of 4x4 units s0 and s0+1 (elements
                         // s0*16 + 4*i4 .. and (s0+1)*16 + 4*i4 ..: block rows 2*s0 + (i4>>1) and 2*s0 + 2 + (i4>>1), columns 4*(i4&1) ..)
                         const uint32_t rlo = is8 ? (uint32_t)rr : (uint32_t)(2 * s0 + (i4 >> 1)), rhi = is8 ? (uint32_t)rr : rlo + 2u;
