@@ -41,7 +41,7 @@ WORKLOAD = 'moflex_400x240'
 BASE_SEED = 1000
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
 # (profiles/): filled in after each capture, None until then.
-NCU_TRAFFIC = {"k_inter": 5.70e8}   # profiles/r01k_prof_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum of one k_inter_chunk launch (415.0 + 154.5 MB)
+NCU_TRAFFIC = {"k_inter": 5.68e8}   # profiles/r01l_prof_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum of one k_inter_chunk launch (414.4 + 154.1 MB)
 
 
 def load_peaks():
