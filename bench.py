@@ -14,7 +14,7 @@ of the S streams of a GPU.
          (mobi_batch_stage), the timed region is mobi_batch_replay only -- the reconstruction kernels.
   e2e    through the reference-facing call: HOST frame bytes in -> native entropy parse -> H2D -> reconstruct ->
          YUV->BGRA on the device -> D2H of the bitmaps into pinned host memory (mobi_batch_submit / _fetch).
-  roofline   the dominant kernel (k_inter: motion compensation + dequant + inverse transforms + add/clip),
+  roofline   the dominant kernel (k_inter_chunk: motion compensation + dequant + inverse transforms + add/clip),
          timed alone with CUDA events on the library's own stream, against the measured HBM copy bandwidth.
   cpu_baseline / --impl reference: the reference's own decoder source compiled for the host
          (oracle/_ref, see oracle/build_ref.py), one independent stream per host thread.
@@ -41,7 +41,7 @@ WORKLOAD = 'moflex_400x240'
 BASE_SEED = 1000
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
 # (profiles/): filled in after each capture, None until then.
-NCU_TRAFFIC = {"k_inter": 5.68e8}   # profiles/r01l_prof_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum of one k_inter_chunk launch (414.4 + 154.1 MB)
+NCU_TRAFFIC = {"k_inter_chunk": 5.68e8}   # profiles/r01l_prof_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum of one k_inter_chunk launch (414.4 + 154.1 MB)
 
 
 def load_peaks():
@@ -300,10 +300,11 @@ def main():
     n_il = max(1, kt['inter_launches'])
     inter_ms = kt['inter_ms'] / n_il
     achieved = (inter_bytes / n_il) / (inter_ms * 1e-3) / 1e9 if inter_ms > 0 else 0.0
-    roofline = {'bound': 'hbm', 'kernel': 'k_inter', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': NCU_TRAFFIC.get('k_inter'), 'algorithmic_bytes_per_launch': inter_bytes / n_il, 'launch_ms': inter_ms,
+    inter_name = 'k_inter' if os.environ.get('MOBI_INTER_KERNEL') == 'warp' else 'k_inter_chunk'   # which inter kernel the library runs
+    roofline = {'bound': 'hbm', 'kernel': inter_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': NCU_TRAFFIC.get(inter_name), 'algorithmic_bytes_per_launch': inter_bytes / n_il, 'launch_ms': inter_ms,
                 'launches_timed': kt['inter_launches'], 'peak_source': peak_src,
-                'step_ms_by_kernel': {'k_inter': kt['inter_ms'] / K, 'k_intra_p_pictures': kt['intra_ms'] / K,
+                'step_ms_by_kernel': {inter_name: kt['inter_ms'] / K, 'k_intra_p_pictures': kt['intra_ms'] / K,
                                       'k_intra_i_pictures_side_stream': kt['key_ms'] / K},
                 'intra_algorithmic_bytes_per_step': intra_bytes / K}
 
