@@ -26,7 +26,7 @@ REF = os.environ.get('MOBI_REFERENCE_DIR', '/root/reference')
 OUT = os.path.join(HERE, '_ref')
 
 PRIMS = r'(?:byte|sbyte|ushort|short|uint|int|ulong|long|float|bool)'
-STATIC_CLASSES = r'(?:IOUtil|MobiConst|Array|Color|ImageLockMode|PixelFormat|MobiclipVersion)'
+STATIC_CLASSES = r'(?:IOUtil|MobiConst|Array|Color|ImageLockMode|PixelFormat|MobiclipVersion|FrameUtil|Math)'
 
 
 def cs_to_cpp(src: str) -> str:
@@ -62,6 +62,49 @@ def cs_to_cpp(src: str) -> str:
     return src
 
 
+def extract_methods(cs: str, names) -> str:
+    """The full text (signature to matching brace) of the named methods of a C# file, in file order.  Used for the
+    reference's SECOND copies of the reconstruction primitives, which live as static helpers inside encoder classes whose
+    remaining members (List / LINQ / Bitmap based mode search) the syntactic transliteration cannot carry."""
+    out = []
+    for m in re.finditer(r'^[ \t]*(?:public|private)\s+(?:static\s+)?(?:unsafe\s+)?(?:static\s+)?[\w\[\]]+\s+(\w+)\s*\([^)]*\)\s*\{', cs, flags=re.M):
+        if m.group(1) not in names:
+            continue
+        depth, i = 0, m.end() - 1
+        while True:
+            c = cs[i]
+            if c == '{':
+                depth += 1
+            elif c == '}':
+                depth -= 1
+                if depth == 0:
+                    break
+            i += 1
+        out.append(cs[m.start():i + 1])
+    return '\n\n'.join(out)
+
+
+def fix_fixed(src: str) -> str:
+    """`fixed (byte* a = x, b = y) {` pins two arrays and declares two pointers; in C++ it becomes a block that opens with
+    the declarations, one per pointer (`byte* a = x, b = y;` would make b a byte).  Initialisers may contain one level of
+    parentheses, which cs_to_cpp's own `fixed` rule does not accept."""
+    def repl(m):
+        ty, decls = m.group(1), m.group(2)
+        parts, depth, cur = [], 0, ''
+        for ch in decls:
+            if ch in '([':
+                depth += 1
+            elif ch in ')]':
+                depth -= 1
+            if ch == ',' and depth == 0:
+                parts.append(cur.strip()); cur = ''
+            else:
+                cur += ch
+        parts.append(cur.strip())
+        return '{ ' + ' '.join('%s* %s;' % (ty, d) for d in parts)
+    return re.sub(r'fixed\s*\(\s*(\w+)\s*\*\s*((?:[^()]|\([^()]*\))*)\)\s*\{', repl, src)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     files = {
@@ -77,6 +120,21 @@ def main():
         with open(os.path.join(OUT, out), 'w') as f:
             f.write('// transliterated at build time from %s -- NOT committed, do not edit\n' % rel)
             f.write(cs_to_cpp(cs))
+    # The reference's second copies of the primitives: FrameUtil (whole file: block get/set and
+    # GetPBlock = CopyBlock's twin), and the static transform / predictor helpers of the encoder classes.
+    second = {
+        'LibMobiclip/Codec/Mobiclip/Encoder/MobiEncoder.cs': ('EncTransforms', ['DCT64', 'IDCT64', 'DCT16', 'IDCT16']),
+        'LibMobiclip/Codec/Mobiclip/Encoder/MacroBlock.cs': ('EncPredictors', ['GetCompvals8x8', 'GetCompvals4x4', 'PredictIntraPlane16x16',
+                                                                              'PredictIntraPlane8x8', 'PredictIntraPlane4x4']),
+    }
+    with open(os.path.join(OUT, 'gen_SecondCopies.h'), 'w') as f:
+        f.write('// transliterated at build time from the reference -- NOT committed, do not edit\n')
+        cs = open(os.path.join(REF, 'LibMobiclip/Utils/FrameUtil.cs'), encoding='utf-8-sig').read()
+        f.write(cs_to_cpp(fix_fixed(cs)))
+        for rel, (cls, names) in second.items():
+            cs = open(os.path.join(REF, rel), encoding='utf-8-sig').read()
+            body = extract_methods(cs, names)
+            f.write('\n' + cs_to_cpp(fix_fixed('namespace LibMobiclip.Codec.Mobiclip.Encoder\n{\n    public class %s\n    {\n%s\n    }\n}\n' % (cls, body))))
     so = os.path.join(OUT, 'libmobiref.so')
     cmd = ['g++', '-std=c++17', '-O2', '-fPIC', '-shared', '-fwrapv', '-ffp-contract=off', '-fno-strict-aliasing',
            '-w', '-fmax-errors=30', '-I', HERE, '-I', OUT, os.path.join(HERE, 'ref_capi.cpp'), '-o', so]

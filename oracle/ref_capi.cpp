@@ -108,3 +108,65 @@ int mobiref_idct(void* h, int plane, int n, const int32_t* coef, int endpos, int
     return 1;
 }
 }  // extern "C"
+
+// ---- the reference's SECOND copies of the primitives: FrameUtil.GetPBlock (twin of CopyBlock),
+// MobiEncoder.IDCT64 / IDCT16 (+ the forward transforms), MacroBlock.GetCompvals8x8 / 4x4 and the three plane
+// predictors.  Compiled from the reference's files like the decoder; tests/test_second_copies.py checks decoder copy
+// == encoder copy == oracle on random inputs. ----
+using namespace LibMobiclip_Codec_Mobiclip;
+#include "gen_SecondCopies.h"
+using LibMobiclip_Codec_Mobiclip_Encoder::EncTransforms;
+using LibMobiclip_Codec_Mobiclip_Encoder::EncPredictors;
+
+namespace {
+template <class T> Arr<T> arr_from(const T* p, int n) { Arr<T> a = Arr<T>::New(n); if (n) std::memcpy(a.raw(), p, (size_t)n * sizeof(T)); return a; }
+}
+
+extern "C" {
+// FrameUtil.GetPBlock(Src, Dx, Dy, Width, Height, Offset, Stride) -> Width*Height bytes.  Returns 0 if it threw.
+int mobiref2_pblock(const uint8_t* src, int len, int dx, int dy, unsigned w, unsigned h, int offset, int stride, uint8_t* out) {
+    try {
+        Arr<byte> r = FrameUtil::GetPBlock(arr_from<byte>(src, len), dx, dy, w, h, offset, stride);
+        std::memcpy(out, r.raw(), (size_t)r.Length);
+        return 1;
+    } catch (...) { return 0; }
+}
+// MobiEncoder.IDCT64 / IDCT16 (DCT[n*n], PPixels[n*n]) -> n*n reconstructed pixels.
+int mobiref2_idct(int n, const int32_t* dct, const uint8_t* pred, uint8_t* out) {
+    try {
+        Arr<int> d = arr_from<int>(dct, n * n);
+        Arr<byte> p = arr_from<byte>(pred, n * n);
+        Arr<byte> r = n == 8 ? EncTransforms::IDCT64(d, p) : EncTransforms::IDCT16(d, p);
+        std::memcpy(out, r.raw(), (size_t)r.Length);
+        return 1;
+    } catch (...) { return 0; }
+}
+// MobiEncoder.DCT64 / DCT16 (InPixels[n*n], residual as int) -> n*n coefficients.
+int mobiref2_fdct(int n, const int32_t* px, int32_t* out) {
+    try {
+        Arr<int> r = n == 8 ? EncTransforms::DCT64(arr_from<int>(px, n * n)) : EncTransforms::DCT16(arr_from<int>(px, n * n));
+        std::memcpy(out, r.raw(), (size_t)r.Length * sizeof(int));
+        return 1;
+    } catch (...) { return 0; }
+}
+// MacroBlock.GetCompvals8x8 / GetCompvals4x4 (BlockType, Data, X, Y, Stride, Offset) -> n*n predicted pixels.
+int mobiref2_compvals(int n, int mode, const uint8_t* data, int len, int x, int y, int stride, int offset, uint8_t* out) {
+    try {
+        Arr<byte> r = n == 8 ? EncPredictors::GetCompvals8x8(mode, arr_from<byte>(data, len), x, y, stride, offset)
+                             : EncPredictors::GetCompvals4x4(mode, arr_from<byte>(data, len), x, y, stride, offset);
+        if (!r.p) return 0;
+        std::memcpy(out, r.raw(), (size_t)r.Length);
+        return r.Length;
+    } catch (...) { return 0; }
+}
+// MacroBlock.PredictIntraPlane16x16 / 8x8 / 4x4 (Data, Offset, Stride, Param) -> n*n predicted pixels.
+int mobiref2_plane(int n, const uint8_t* data, int len, int offset, int stride, int param, uint8_t* out) {
+    try {
+        Arr<byte> d = arr_from<byte>(data, len);
+        Arr<byte> r = n == 16 ? EncPredictors::PredictIntraPlane16x16(d, offset, stride, param)
+                    : n == 8 ? EncPredictors::PredictIntraPlane8x8(d, offset, stride, param) : EncPredictors::PredictIntraPlane4x4(d, offset, stride, param);
+        std::memcpy(out, r.raw(), (size_t)r.Length);
+        return r.Length;
+    } catch (...) { return 0; }
+}
+}  // extern "C"

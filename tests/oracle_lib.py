@@ -195,3 +195,58 @@ class Ref(_CpuDecoder):
             self.L.mobiref_destroy(self.h)
         except Exception:
             pass
+
+
+class Ref2:
+    """The reference's SECOND copies of the reconstruction primitives, compiled from its own files
+    like the decoder (oracle/build_ref.py): FrameUtil.GetPBlock, MobiEncoder.IDCT64 / IDCT16 / DCT64 / DCT16,
+    MacroBlock.GetCompvals8x8 / 4x4 and PredictIntraPlane16x16 / 8x8 / 4x4.  Stateless."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(REF_SO)
+            L.mobiref2_pblock.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p]
+            L.mobiref2_idct.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.mobiref2_fdct.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+            L.mobiref2_compvals.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+            L.mobiref2_plane.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def pblock(cls, src, dx, dy, w, h, offset, stride):
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        out = np.zeros(w * h, dtype=np.uint8)
+        ok = cls.lib().mobiref2_pblock(src.ctypes.data, src.size, dx, dy, w, h, offset, stride, out.ctypes.data)
+        return out.reshape(h, w) if ok else None
+
+    @classmethod
+    def idct(cls, n, coef, pred):
+        coef = np.ascontiguousarray(coef, dtype=np.int32)
+        pred = np.ascontiguousarray(pred, dtype=np.uint8)
+        out = np.zeros(n * n, dtype=np.uint8)
+        ok = cls.lib().mobiref2_idct(n, coef.ctypes.data, pred.ctypes.data, out.ctypes.data)
+        return out.reshape(n, n) if ok else None
+
+    @classmethod
+    def fdct(cls, n, px):
+        px = np.ascontiguousarray(px, dtype=np.int32)
+        out = np.zeros(n * n, dtype=np.int32)
+        ok = cls.lib().mobiref2_fdct(n, px.ctypes.data, out.ctypes.data)
+        return out if ok else None
+
+    @classmethod
+    def compvals(cls, n, mode, data, x, y, stride, offset=0):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.zeros(n * n, dtype=np.uint8)
+        k = cls.lib().mobiref2_compvals(n, mode, data.ctypes.data, data.size, x, y, stride, offset, out.ctypes.data)
+        return out.reshape(n, n) if k == n * n else None
+
+    @classmethod
+    def plane(cls, n, data, offset, stride, param):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.zeros(n * n, dtype=np.uint8)
+        k = cls.lib().mobiref2_plane(n, data.ctypes.data, data.size, offset, stride, param, out.ctypes.data)
+        return out.reshape(n, n) if k == n * n else None
