@@ -154,6 +154,7 @@ def cpu_decode_fps(streams, w, h, ver, threads, budget_s, want_bgra=True):
 
 
 def main():
+    global WORKLOAD, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -165,7 +166,13 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--profile', action='store_true', help='short run for ncu: value leg only')
+    ap.add_argument('--workload', default=WORKLOAD, help='synthetic workload (mobiclipdecoder_b200/workloads.py); the default is the one the metric is quoted on, '
+                    'mods_256x192 (config 1) and moc5_640x480 (config 4) are reported beside it in BASELINE.md')
     args = ap.parse_args()
+    if args.workload != WORKLOAD:
+        from mobiclipdecoder_b200.workloads import CONFIGS as _C
+        WORKLOAD = args.workload
+        METRIC = 'mobiclip_frames_per_sec_%dx%d' % (_C[WORKLOAD][0], _C[WORKLOAD][1])
 
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -362,8 +369,8 @@ def main():
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms / K,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/int32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'width': w, 'height': h, 'version': 'Moflex3DS', 'streams_per_gpu': S, 'frames_per_step': S * world,
-                       'gop': 90, 'l2_policy': 'inputs larger than L2: each step touches %.0f MB of pictures per GPU' % (2 * S * 512 * h * 1.5 / 1e6),
+            'config': {'workload': WORKLOAD, 'width': w, 'height': h, 'version': ver.name, 'streams_per_gpu': S, 'frames_per_step': S * world,
+                       'gop': CONFIGS[WORKLOAD][3].get('gop'), 'l2_policy': 'inputs larger than L2: each step touches %.0f MB of pictures per GPU' % (2 * S * (256 if w <= 256 else 512 if w <= 512 else 1024) * h * 1.5 / 1e6),
                        'mix_per_step': {'inter_mbs': d['inter_mbs'] / K, 'intra_mbs': d['intra_mbs'] / K, 'partitions': d['parts'] / K, 'coefs': d['coefs'] / K}},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'e2e_variants': e2e_variants, 'gpu_launches': launches_value, 'clocks': clocks,
             'host': {'cores': cores, 'parse_threads_per_gpu': threads, 'stream_generation_s': t_gen, 'staged_h2d_bytes': staged_h2d},
