@@ -1,0 +1,34 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/primitives_second_copies.json: SHA-256 digests of the outputs of the reference's SECOND
+(encoder-side) copies of the reconstruction primitives -- FrameUtil.GetPBlock, MobiEncoder.IDCT64 / IDCT16,
+MacroBlock.GetCompvals8x8 / 4x4, MacroBlock.PredictIntraPlane16x16 / 8x8 / 4x4, compiled from the reference's files by
+oracle/build_ref.py -- on seeded random inputs.  tests/test_golden_primitives.py regenerates the same inputs and checks
+the ORACLE's primitives against the digests, so the pin holds where neither /root/reference nor oracle/_ref exists.
+
+    python tools/make_golden_primitives.py
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+
+def main():
+    from mobiclipdecoder_b200 import _build
+    _build.build_all()
+    from oracle_lib import have_ref
+    if not have_ref():
+        raise SystemExit('oracle/_ref/libmobiref.so is not built: these digests come from the compiled reference source only')
+    import primitive_cases as pc
+    out = {'made_by': 'tools/make_golden_primitives.py', 'source': 'reference second copies (oracle/build_ref.py: gen_SecondCopies.h)', 'digests': pc.digests(pc.run_second_copies)}
+    path = os.path.join(ROOT, 'tests', 'golden', 'primitives_second_copies.json')
+    with open(path, 'w') as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print('wrote', path, {k: v[:12] for k, v in out['digests'].items()})
+
+
+if __name__ == '__main__':
+    main()
