@@ -70,8 +70,10 @@ def gen_streams(n_streams, n_frames, first_seed, threads):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe)."""
-    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  The process is started
+    early (its start-up must not fall into a timed region); only the samples between the first and the last mark() --
+    the start of the value leg and the end of the end-to-end legs -- are reported."""
+    Q = 'timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, gpu_index):
@@ -87,9 +89,18 @@ class ClockSampler:
     def mark(self):
         self.marks.append(time.time())
 
+    @staticmethod
+    def _when(stamp):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp, '%Y/%m/%d %H:%M:%S.%f').timestamp()
+        except ValueError:
+            return None
+
     def stop(self):
         if self.p is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.mark()
         time.sleep(0.15)
         self.p.terminate()
         try:
@@ -100,18 +111,21 @@ class ClockSampler:
         rows = []
         for line in open(self.f.name):
             parts = [x.strip() for x in line.split(',')]
-            if len(parts) >= 7:
+            if len(parts) >= 8:
                 try:
-                    rows.append((float(parts[0]), float(parts[1]), parts[3:7]))
+                    rows.append((self._when(parts[0]), float(parts[1]), float(parts[2]), parts[4:8]))
                 except ValueError:
                     pass
         os.unlink(self.f.name)
         if not rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
-        sm = sorted(r[0] for r in rows)
+        lo, hi = self.marks[0], self.marks[-1]
+        busy = [r for r in rows if r[0] is not None and lo - 0.05 <= r[0] <= hi + 0.05]
+        rows = busy if busy else rows[len(rows) // 2:]   # (timestamps unreadable: the later half covers the timed legs, stop() follows them)
+        sm = sorted(r[1] for r in rows)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in rows for i, v in enumerate(r[2]) if v.lower().startswith('active')})
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': rows[0][1], 'reasons': reasons, 'samples': len(rows)}
+        reasons = sorted({names[i] for r in rows for i, v in enumerate(r[3]) if v.lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': rows[0][2], 'reasons': reasons, 'samples': len(rows)}
 
 
 def cpu_decode_fps(streams, w, h, ver, threads, budget_s, want_bgra=True):
@@ -246,6 +260,10 @@ def main():
     t_gen = time.time() - t_gen
     bitstream_bytes = sum(len(f) for st in streams for f in st)
 
+    # nvidia-smi is started well before the timed regions: its start-up (NVML initialisation over every GPU of the node)
+    # takes driver locks that can hold up kernel launches of ANY rank for a millisecond or more -- seen once as a 20 %
+    # slower value leg on one of eight ranks when it was started right in front of the 7 ms timed region
+    sampler = ClockSampler(local_rank) if rank == 0 and not args.profile else None
     batch = MobiBatch(w, h, ver, S, device=local_rank, n_threads=threads)
     ext = torch.cuda.ExternalStream(batch.cuda_stream(), device=dev)
 
@@ -270,7 +288,8 @@ def main():
         batch.sync()
         print(json.dumps({'profile': True, 'steps': K, 'streams': S}))
         return 0
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     st0 = batch.stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sharding.barrier(dist if world > 1 else None, local_rank)
