@@ -47,7 +47,8 @@ def sass_rows(rep, name_part, n_instr):
         title = rows[max(i for i in names if i < hi)][1]
         end = min([i for i in names if i > hi] + [len(rows)])
         body = [r for r in rows[hi + 1:end] if len(r) == len(rows[hi])]
-        if name_part.split('ILi')[0].lstrip('0123456789') in title and len(body) == n_instr:
+        name = re.split(r'EPK|ILi', name_part.lstrip('0123456789'))[0]   # mangled fragment -> plain kernel name
+        if re.search(r'::%s[(<]' % re.escape(name), title) and len(body) == n_instr:
             return rows[hi], body, title
     raise SystemExit('no launch of %s with %d instructions in %s' % (name_part, n_instr, rep))
 
