@@ -26,7 +26,7 @@ REF = os.environ.get('MOBI_REFERENCE_DIR', '/root/reference')
 OUT = os.path.join(HERE, '_ref')
 
 PRIMS = r'(?:byte|sbyte|ushort|short|uint|int|ulong|long|float|bool)'
-STATIC_CLASSES = r'(?:IOUtil|MobiConst|Array|Color|ImageLockMode|PixelFormat|MobiclipVersion|FrameUtil|Math)'
+STATIC_CLASSES = r'(?:IOUtil|MobiConst|MobiConstRef|Array|Color|ImageLockMode|PixelFormat|MobiclipVersion|FrameUtil|Math)'
 
 
 def cs_to_cpp(src: str) -> str:
@@ -42,6 +42,7 @@ def cs_to_cpp(src: str) -> str:
     src = re.sub(r'new\s+(%s)\[([^\]]+)\]\[\]' % PRIMS, r'Arr<Arr<\1>>::New(\2)', src)
     src = re.sub(r'new\s+(%s)\[([^\]]+)\]' % PRIMS, r'Arr<\1>::New(\2)', src)
     src = re.sub(r'new\s+(Bitmap|Rectangle|Exception|NotImplementedException)\s*\(', r'\1(', src)
+    src = re.sub(r'new\s+(List<\w+>)\s*\(', r'\1(', src)
     # array types
     src = re.sub(r'\b(%s)\[\]\[\]' % PRIMS, r'Arr<Arr<\1>>', src)
     src = re.sub(r'\b(%s)\[\]' % PRIMS, r'Arr<\1>', src)
@@ -135,9 +136,30 @@ def main():
             cs = open(os.path.join(REF, rel), encoding='utf-8-sig').read()
             body = extract_methods(cs, names)
             f.write('\n' + cs_to_cpp(fix_fixed('namespace LibMobiclip.Codec.Mobiclip.Encoder\n{\n    public class %s\n    {\n%s\n    }\n}\n' % (cls, body))))
+    # The reference's own bit writer and coefficient entropy CODER (BitWriter.cs whole; MobiEncoder.EncodeDCT, which uses no
+    # instance state; the [32, 64, 2] reverse code table of MobiConst.cs that cs_to_cpp drops from the decoder build): an
+    # independent writer for the streams the parsers are tested on (tests/test_reference_entropy_writer.py).
+    with open(os.path.join(OUT, 'gen_EntropyWriter.h'), 'w') as f:
+        f.write('// transliterated at build time from the reference -- NOT committed, do not edit\n')
+        mc = open(os.path.join(REF, 'LibMobiclip/Codec/Mobiclip/MobiConst.cs'), encoding='utf-8-sig').read()
+        m = re.search(r'public static readonly int\[, ,\] VxTable0_A_Ref\s*=\s*(\{.*?\n        \});', mc, flags=re.S)
+        table = eval(m.group(1).rstrip(';').replace('{', '[').replace('}', ']'))
+        d0, d1, d2 = len(table), len(table[0]), len(table[0][0])
+        assert all(len(r) == d1 and all(len(c) == d2 for c in r) for r in table)
+        f.write('struct MobiConstRef {\n    static int At(long long a, long long b, long long c) {\n')
+        f.write('        static const int T[%d][%d][%d] = %s;\n' % (d0, d1, d2, m.group(1).rstrip(';')))
+        f.write('        if (a < 0 || a >= %d || b < 0 || b >= %d || c < 0 || c >= %d) throw IndexOutOfRangeException();\n        return T[a][b][c];\n    }\n};\n' % (d0, d1, d2))
+        f.write(cs_to_cpp(open(os.path.join(REF, 'LibMobiclip/Codec/Mobiclip/BitWriter.cs'), encoding='utf-8-sig').read()))
+        enc = extract_methods(open(os.path.join(REF, 'LibMobiclip/Codec/Mobiclip/Encoder/MobiEncoder.cs'), encoding='utf-8-sig').read(), ['EncodeDCT'])
+        enc = enc.replace('private void EncodeDCT', 'public static void EncodeDCT').replace('BitWriter b)', 'BitWriterRef b)')
+        enc = re.sub(r'MobiConst\.VxTable0_A_Ref\[(.*?)\]', r'MobiConstRef.At(\1)', enc)
+        # C++ does not let `goto end` jump over an initialised declaration in the same scope; split it (no logic changes)
+        enc = enc.replace('int newval = val -', 'int newval; newval = val -')
+        f.write('\ntypedef LibMobiclip_Codec_Mobiclip::BitWriter& BitWriterRef;\n')
+        f.write(cs_to_cpp('namespace LibMobiclip.Codec.Mobiclip.Encoder\n{\n    public class EncEntropy\n    {\n%s\n    }\n}\n' % enc))
     so = os.path.join(OUT, 'libmobiref.so')
     cmd = ['g++', '-std=c++17', '-O2', '-fPIC', '-shared', '-fwrapv', '-ffp-contract=off', '-fno-strict-aliasing',
-           '-w', '-fmax-errors=30', '-I', HERE, '-I', OUT, os.path.join(HERE, 'ref_capi.cpp'), '-o', so]
+           '-w', '-fpermissive', '-fmax-errors=30', '-I', HERE, '-I', OUT, os.path.join(HERE, 'ref_capi.cpp'), '-o', so]
     print(' '.join(cmd))
     subprocess.check_call(cmd)
     print('built', so)

@@ -170,3 +170,28 @@ int mobiref2_plane(int n, const uint8_t* data, int len, int offset, int stride, 
     } catch (...) { return 0; }
 }
 }  // extern "C"
+
+// ---- the reference's bit writer and coefficient entropy coder (BitWriter.cs, MobiEncoder.EncodeDCT ME:675-765):
+// an independent writer for bitstreams the parsers are tested on. ----
+#include "gen_EntropyWriter.h"
+using LibMobiclip_Codec_Mobiclip::BitWriter;
+using LibMobiclip_Codec_Mobiclip_Encoder::EncEntropy;
+
+extern "C" {
+void* mobiref2_bw_create() { return new BitWriter(); }
+void mobiref2_bw_destroy(void* h) { delete (BitWriter*)h; }
+void mobiref2_bw_bits(void* h, unsigned value, int nbits) { ((BitWriter*)h)->WriteBits(value, nbits); }
+void mobiref2_bw_uvar(void* h, unsigned value) { ((BitWriter*)h)->WriteVarIntUnsigned(value); }
+void mobiref2_bw_svar(void* h, int value) { ((BitWriter*)h)->WriteVarIntSigned(value); }
+// EncodeDCT(DCT, Table, b): DCT = quantised levels in SCAN order (n = 64 or 16).  Returns 0 if the reference threw.
+int mobiref2_bw_dct(void* h, const int32_t* dct, int n, int table) {
+    try { EncEntropy::EncodeDCT(arr_from<int>(dct, n), table, *(BitWriter*)h); return 1; } catch (...) { return 0; }
+}
+// ToArray(): flushes and returns the byte count (the bytes if they fit into cap).
+int mobiref2_bw_bytes(void* h, uint8_t* out, int cap) {
+    Arr<byte> a = ((BitWriter*)h)->ToArray();
+    if (a.Length <= cap && a.Length) std::memcpy(out, a.raw(), (size_t)a.Length);
+    return a.Length;
+}
+}  // extern "C"
+

@@ -60,6 +60,19 @@ struct Array {
     }
 };
 
+// ---- System.Collections.Generic.List<T>, as far as BitWriter.cs uses it (reference semantics like the managed type) ----
+template <class T>
+struct List {
+    std::shared_ptr<std::vector<T>> p = std::make_shared<std::vector<T>>();
+    void Add(T x) { p->push_back(x); }
+    void AddRange(const List& o) { p->insert(p->end(), o.p->begin(), o.p->end()); }
+    Arr<T> ToArray() const {
+        Arr<T> a = Arr<T>::New((long long)p->size());
+        if (!p->empty()) std::memcpy(a.raw(), p->data(), p->size() * sizeof(T));
+        return a;
+    }
+};
+
 // ---- System.Drawing stand-ins (pixel container only) ----
 struct Rectangle { int X, Y, Width, Height; Rectangle(int x, int y, int w, int h) : X(x), Y(y), Width(w), Height(h) {} };
 enum class ImageLockMode { WriteOnly };

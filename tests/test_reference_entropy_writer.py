@@ -1,0 +1,54 @@
+"""Known-answer test for the entropy half of the path against the reference's own WRITER: pictures whose bits come from
+BitWriter.cs and MobiEncoder.EncodeDCT (compiled from the reference, tests/ref_entropy_frames.py) must (1) decode to
+the same planes in the compiled reference decoder and in the oracle, (2) parse, in the product's host parser
+(libmobicuda.so, no GPU needed), into exactly the coefficient records that were handed to EncodeDCT -- level, scan
+position, block and sub-block tags, 8x8 / 4x4 -- and (3) reconstruct to the same planes on the GPU."""
+import numpy as np
+import pytest
+
+from oracle_lib import Oracle, Ref, have_ref
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason='oracle/_ref/libmobiref.so not built (needs /root/reference)')
+
+CASES = [(64, 48, 1, 12), (64, 48, 2, 18), (256, 192, 3, 12), (400, 240, 4, 14)]
+
+
+@pytest.mark.parametrize('w,h,seed,q', CASES)
+def test_reference_written_picture_decodes_alike_and_parses_to_what_was_written(w, h, seed, q):
+    from mobiclipdecoder_b200 import MobiParser
+    from ref_entropy_frames import make_i_picture
+    data, want = make_i_picture(w, h, seed, q)
+    r, o = Ref(w, h, 2), Oracle(w, h, 2)
+    ok_r, off_r, bgra_r = r.decode(data, 0)
+    ok_o, off_o, bgra_o = o.decode(data, 0)
+    assert ok_r and ok_o and off_r == off_o
+    assert np.array_equal(r.y, o.y) and np.array_equal(r.uv, o.uv) and np.array_equal(bgra_r, bgra_o)
+    par = MobiParser(w, h, 2)
+    rc, off, pf = par.parse(data, 0)
+    assert rc == 0 and off == off_r
+    hdr = pf.hdr.contents
+    assert hdr.n_coefs == len(want) and hdr.quantizer == q
+    got = []
+    for i in range(hdr.n_coefs):
+        c = pf.coefs[i]
+        got.append((c.blk & 7, c.blk >> 7, (c.pos >> 6) if not (c.blk >> 7) else 0, c.pos & 63, c.level))
+    assert got == want
+    # escape forms were really exercised: levels beyond the 31 the plain table reaches, and runs it has no code for
+    assert max(abs(x[4]) for x in want) > 31
+    par.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('w,h,seed,q', CASES)
+def test_reference_written_picture_on_the_gpu(w, h, seed, q):
+    from mobiclipdecoder_b200 import MobiclipDecoder
+    from ref_entropy_frames import make_i_picture
+    data, want = make_i_picture(w, h, seed, q)
+    o, d = Oracle(w, h, 2), MobiclipDecoder(w, h, 2)
+    ok, off, bgra = o.decode(data, 0)
+    assert ok
+    d.Data, d.Offset = data, 0
+    bmp = d.DecodeFrame()
+    assert bmp is not None and d.Offset == off
+    assert np.array_equal(d.Y[0], o.y) and np.array_equal(d.UV[0], o.uv) and np.array_equal(bmp, bgra)
+    d.close()
