@@ -12,7 +12,7 @@ from mobiclipdecoder_b200.workloads import frames
 from oracle_lib import Oracle
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', '*.json'))
-                if not os.path.basename(p).startswith('primitives_'))   # stream-level files; primitives_*.json: test_golden_primitives.py
+                if not os.path.basename(p).startswith(('primitives_', 'tables_')))   # stream-level files only (primitives_*.json, tables_*.json: test_golden_primitives.py)
 
 
 def _sha(a):

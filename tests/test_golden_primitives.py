@@ -14,3 +14,33 @@ def test_oracle_primitives_match_the_references_second_copies():
     want = json.load(open(PATH))['digests']
     got = pc.digests(pc.run_oracle)
     assert got == want
+
+
+def test_partition_code_tables_match_the_encoders_inverse_tables():
+    """The decoder reads partition trees through 16 peek tables per version (MobiclipDecoder.cs:458-1746, extracted into
+    mobi_tables.h MOBI_PART_CODE); the reference's encoder writes them from inverse (value, bits) tables of its own
+    (Analyzer.cs:472-526, Moflex3DS only; frozen in tests/golden/tables_partition_encoder.json).  Every code the encoder can
+    write must read back as its symbol with the same length, for every completion of the peeked bits, and the encoder must
+    know exactly the symbols the decoder accepts."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    enc = json.load(open(os.path.join(os.path.dirname(PATH), 'tables_partition_encoder.json')))
+    txt = open(os.path.join(root, 'mobiclipdecoder_b200', 'csrc', 'mobi_tables.h')).read()
+    body = txt[txt.index('MOBI_PART_CODE[2][4][4]'):]
+    entries = re.findall(r'\{(\d+), \{([\d,]+)\}, \{([\d,]+)\}\}', body)
+    assert len(entries) >= 16
+    checked = 0
+    for lw in range(4):
+        for lh in range(4):
+            peek, lens, syms = entries[lw * 4 + lh]          # version 0 = Moflex3DS comes first
+            peek, lens, syms = int(peek), [int(x) for x in lens.split(',')], [int(x) for x in syms.split(',')]
+            for s in range(10):
+                bits, val = enc['bits'][lw][lh][s], enc['value'][lw][lh][s]
+                if bits < 0:
+                    assert lens[s] == 0, 'shape %d,%d: the decoder accepts symbol %d, the encoder cannot write it' % (lw, lh, s)
+                    continue
+                assert lens[s] == bits and bits <= peek
+                for fill in range(1 << (peek - bits)):
+                    assert syms[(val << (peek - bits)) | fill] == s
+                checked += 1
+    assert checked > 100

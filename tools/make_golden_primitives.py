@@ -28,6 +28,18 @@ def main():
     with open(path, 'w') as f:
         json.dump(out, f, indent=1, sort_keys=True)
     print('wrote', path, {k: v[:12] for k, v in out['digests'].items()})
+    # the encoder's inverse partition-tree code tables (Analyzer.cs:472-526, Moflex3DS): [log2 w - 1][log2 h - 1][symbol] -> (value, bits)
+    import re
+    an = open('/root/reference/LibMobiclip/Codec/Mobiclip/Analyzer.cs', encoding='utf-8-sig').read()
+
+    def table(name):
+        m = re.search(r'%s = new int\[4, 4, 10\]\s*(\{.*?\n            \});' % name, an, flags=re.S)
+        return eval(m.group(1).rstrip(';').replace('{', '[').replace('}', ']'))
+    tabs = {'source': 'LibMobiclip/Codec/Mobiclip/Analyzer.cs:472-526 (HuffEncodeValTable, HuffEncodeBitTable)', 'value': table('HuffEncodeValTable'), 'bits': table('HuffEncodeBitTable')}
+    path = os.path.join(ROOT, 'tests', 'golden', 'tables_partition_encoder.json')
+    with open(path, 'w') as f:
+        json.dump(tabs, f, sort_keys=True)
+    print('wrote', path)
 
 
 if __name__ == '__main__':
