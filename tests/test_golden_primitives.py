@@ -44,3 +44,23 @@ def test_partition_code_tables_match_the_encoders_inverse_tables():
                     assert syms[(val << (peek - bits)) | fill] == s
                 checked += 1
     assert checked > 100
+
+
+def test_coded_block_pattern_tables_match_the_encoders_inverse_tables():
+    """byte_116160 / byte_1165C4 (inter, MD:1809, 2904) and byte_115FC4 / byte_1164F4 (intra, MD:1748, 2863) map a varint to a
+    coded-block pattern; the encoder holds the inverse maps (MobiEncoder.cs:149-161, 407-415).  decoder[encoder[p]] == p for
+    every pattern the encoder can write."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    enc = json.load(open(os.path.join(os.path.dirname(PATH), 'tables_partition_encoder.json')))
+    txt = open(os.path.join(root, 'mobiclipdecoder_b200', 'csrc', 'mobi_tables.h')).read()
+
+    def dec(name):
+        body = re.search(r'%s\[\d+\] = \{(.*?)\};' % name, txt, flags=re.S).group(1)
+        return [int(x, 0) for x in re.findall(r'0x[0-9A-Fa-f]+|\d+', body)]
+    for dname, ename, n in (('MOBI_CBP6_INTER', 'REV_byte_116160', 64), ('MOBI_CBP4_INTER', 'REV_byte_1165C4', 16),
+                            ('MOBI_CBP6_INTRA', 'REV_byte_115FC4', 64), ('MOBI_CBP4_INTRA', 'REV_byte_1164F4', 16)):
+        d, e = dec(dname), enc[ename]
+        assert len(e) == n
+        for pattern in range(n):
+            assert d[e[pattern]] == pattern, (dname, pattern)

@@ -36,6 +36,12 @@ def main():
         m = re.search(r'%s = new int\[4, 4, 10\]\s*(\{.*?\n            \});' % name, an, flags=re.S)
         return eval(m.group(1).rstrip(';').replace('{', '[').replace('}', ']'))
     tabs = {'source': 'LibMobiclip/Codec/Mobiclip/Analyzer.cs:472-526 (HuffEncodeValTable, HuffEncodeBitTable)', 'value': table('HuffEncodeValTable'), 'bits': table('HuffEncodeBitTable')}
+    # the encoder's inverse coded-block-pattern tables (MobiEncoder.cs:149-161, 407-415): pattern -> varint value
+    me = open('/root/reference/LibMobiclip/Codec/Mobiclip/Encoder/MobiEncoder.cs', encoding='utf-8-sig').read()
+    for name in ('REV_byte_116160', 'REV_byte_1165C4', 'REV_byte_115FC4', 'REV_byte_1164F4'):
+        m = re.search(r'%s\s*=\s*\{(.*?)\};' % name, me, flags=re.S)
+        tabs[name] = [int(x) for x in re.findall(r'\d+', m.group(1))]
+    tabs['source_cbp'] = 'LibMobiclip/Codec/Mobiclip/Encoder/MobiEncoder.cs:149-161, 407-415'
     path = os.path.join(ROOT, 'tests', 'golden', 'tables_partition_encoder.json')
     with open(path, 'w') as f:
         json.dump(tabs, f, sort_keys=True)
