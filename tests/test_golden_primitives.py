@@ -64,3 +64,26 @@ def test_coded_block_pattern_tables_match_the_encoders_inverse_tables():
         assert len(e) == n
         for pattern in range(n):
             assert d[e[pattern]] == pattern, (dname, pattern)
+
+
+def test_dequantisation_tables_match_the_encoders_setup():
+    """MobiEncoder.SetupQuantizationTables (ME:930-960) builds its scale tables from its own copies of the constant tables:
+    scale4[pos] = (byte_118F94[(q % 6) * 16 + pos] << (q / 6 + 8)) >> 8, scale8[pos] = (byte_118DD4[(q % 6) * 64 + pos] << (q / 6 + 6)) >> 8
+    (q / 6 and q % 6 through byte_119004 / byte_11903A).  The product's host parser must hand the kernels exactly these
+    scales for every legal quantiser (hdr.qtab = scale << 8 | position, MD:3897-3912)."""
+    from mobiclipdecoder_b200 import MobiParser
+    from mobiclipdecoder_b200.workloads import frames
+    enc = json.load(open(os.path.join(os.path.dirname(PATH), 'tables_partition_encoder.json')))
+    t8, t4, div6, mod6 = enc['enc_byte_118DD4'], enc['enc_byte_118F94'], enc['enc_byte_119004'], enc['enc_byte_11903A']
+    assert len(t8) == 384 and len(t4) == 96 and len(div6) >= 53 and len(mod6) >= 53
+    for q in range(12, 47):   # the stream generator writes quantisers 12..46
+        (data, key), = frames('moflex_400x240', 3, 1, quant=q)
+        par = MobiParser(400, 240, 2)
+        rc, off, pf = par.parse(data, 0)
+        assert rc == 0 and pf.hdr.contents.quantizer == q
+        qtab = list(pf.hdr.contents.qtab)
+        for pos in range(64):
+            assert qtab[pos] >> 8 == (t8[mod6[q] * 64 + pos] << (div6[q] + 6)) >> 8, (q, pos)
+        for pos in range(16):
+            assert qtab[64 + pos] >> 8 == (t4[mod6[q] * 16 + pos] << (div6[q] + 8)) >> 8, (q, pos)
+        par.close()

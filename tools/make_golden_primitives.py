@@ -42,6 +42,11 @@ def main():
         m = re.search(r'%s\s*=\s*\{(.*?)\};' % name, me, flags=re.S)
         tabs[name] = [int(x) for x in re.findall(r'\d+', m.group(1))]
     tabs['source_cbp'] = 'LibMobiclip/Codec/Mobiclip/Encoder/MobiEncoder.cs:149-161, 407-415'
+    # the encoder's own copies of the dequantisation tables (MobiEncoder.cs:862-917) behind its SetupQuantizationTables (:930-960)
+    for name in ('byte_118DD4', 'byte_118F94', 'byte_119004', 'byte_11903A'):
+        m = re.search(r'byte\[\] %s\s*=\s*\{(.*?)\};' % name, me, flags=re.S)
+        tabs['enc_' + name] = [int(x, 16) for x in re.findall(r'0x([0-9A-Fa-f]+)', m.group(1))]
+    tabs['source_quant'] = 'LibMobiclip/Codec/Mobiclip/Encoder/MobiEncoder.cs:862-960'
     path = os.path.join(ROOT, 'tests', 'golden', 'tables_partition_encoder.json')
     with open(path, 'w') as f:
         json.dump(tabs, f, sort_keys=True)
