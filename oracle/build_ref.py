@@ -143,7 +143,8 @@ def main():
         f.write('// transliterated at build time from the reference -- NOT committed, do not edit\n')
         mc = open(os.path.join(REF, 'LibMobiclip/Codec/Mobiclip/MobiConst.cs'), encoding='utf-8-sig').read()
         m = re.search(r'public static readonly int\[, ,\] VxTable0_A_Ref\s*=\s*(\{.*?\n        \});', mc, flags=re.S)
-        table = eval(m.group(1).rstrip(';').replace('{', '[').replace('}', ']'))
+        import ast
+        table = ast.literal_eval(m.group(1).rstrip(';').replace('{', '[').replace('}', ']'))   # integer literals only; never eval() reference text
         d0, d1, d2 = len(table), len(table[0]), len(table[0][0])
         assert all(len(r) == d1 and all(len(c) == d2 for c in r) for r in table)
         f.write('struct MobiConstRef {\n    static int At(long long a, long long b, long long c) {\n')

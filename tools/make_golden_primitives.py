@@ -34,7 +34,9 @@ def main():
 
     def table(name):
         m = re.search(r'%s = new int\[4, 4, 10\]\s*(\{.*?\n            \});' % name, an, flags=re.S)
-        return eval(m.group(1).rstrip(';').replace('{', '[').replace('}', ']'))
+        import ast
+        txt = re.sub(r'(\d+)\s*>>\s*(\d+)', lambda k: str(int(k.group(1)) >> int(k.group(2))), m.group(1).rstrip(';'))   # the only operator in the table
+        return ast.literal_eval(txt.replace('{', '[').replace('}', ']'))   # integer literals only; never eval() reference text
     tabs = {'source': 'LibMobiclip/Codec/Mobiclip/Analyzer.cs:472-526 (HuffEncodeValTable, HuffEncodeBitTable)', 'value': table('HuffEncodeValTable'), 'bits': table('HuffEncodeBitTable')}
     # the encoder's inverse coded-block-pattern tables (MobiEncoder.cs:149-161, 407-415): pattern -> varint value
     me = open('/root/reference/LibMobiclip/Codec/Mobiclip/Encoder/MobiEncoder.cs', encoding='utf-8-sig').read()
