@@ -1,12 +1,12 @@
 #!/bin/bash
-# Parity + kernel-only bench of the inter-kernel variants, then one full ncu capture (with source counters) of each.
+# Parity + kernel-only bench of the inter kernel (MOBI_INTER_KERNEL: anything but "warp" = k_inter_chunk), then one full ncu capture with source counters.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi -L; nproc
 for k in ${KERNELS:-chunk}; do
   echo "=== pytest -m gpu MOBI_INTER_KERNEL=$k"; MOBI_INTER_KERNEL=$k timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
 done
-for k in ${BENCH_KERNELS:-chunk run2}; do
+for k in ${BENCH_KERNELS:-chunk warp}; do
   echo "=== bench $k"; MOBI_INTER_KERNEL=$k timeout 400 python bench.py --no-e2e --no-cpu > gpurun_out/bench_$k.json 2> gpurun_out/bench_$k.err
   python - <<PY
 import json
