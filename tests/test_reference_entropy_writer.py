@@ -10,20 +10,20 @@ from oracle_lib import Oracle, Ref, have_ref
 
 pytestmark = pytest.mark.skipif(not have_ref(), reason='oracle/_ref/libmobiref.so not built (needs /root/reference)')
 
-CASES = [(64, 48, 1, 12), (64, 48, 2, 18), (256, 192, 3, 12), (400, 240, 4, 14)]
+CASES = [(64, 48, 1, 12, 2), (64, 48, 2, 18, 2), (256, 192, 3, 12, 2), (400, 240, 4, 14, 2), (256, 192, 8, 16, 1), (64, 48, 9, 13, 1)]   # last field: 2 Moflex3DS, 1 ModsDS
 
 
-@pytest.mark.parametrize('w,h,seed,q', CASES)
-def test_reference_written_picture_decodes_alike_and_parses_to_what_was_written(w, h, seed, q):
+@pytest.mark.parametrize('w,h,seed,q,ver', CASES)
+def test_reference_written_picture_decodes_alike_and_parses_to_what_was_written(w, h, seed, q, ver):
     from mobiclipdecoder_b200 import MobiParser
     from ref_entropy_frames import make_i_picture
     data, want = make_i_picture(w, h, seed, q)
-    r, o = Ref(w, h, 2), Oracle(w, h, 2)
+    r, o = Ref(w, h, ver), Oracle(w, h, ver)
     ok_r, off_r, bgra_r = r.decode(data, 0)
     ok_o, off_o, bgra_o = o.decode(data, 0)
     assert ok_r and ok_o and off_r == off_o
     assert np.array_equal(r.y, o.y) and np.array_equal(r.uv, o.uv) and np.array_equal(bgra_r, bgra_o)
-    par = MobiParser(w, h, 2)
+    par = MobiParser(w, h, ver)
     rc, off, pf = par.parse(data, 0)
     assert rc == 0 and off == off_r
     hdr = pf.hdr.contents
@@ -39,12 +39,12 @@ def test_reference_written_picture_decodes_alike_and_parses_to_what_was_written(
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('w,h,seed,q', CASES)
-def test_reference_written_picture_on_the_gpu(w, h, seed, q):
+@pytest.mark.parametrize('w,h,seed,q,ver', CASES)
+def test_reference_written_picture_on_the_gpu(w, h, seed, q, ver):
     from mobiclipdecoder_b200 import MobiclipDecoder
     from ref_entropy_frames import make_i_picture
     data, want = make_i_picture(w, h, seed, q)
-    o, d = Oracle(w, h, 2), MobiclipDecoder(w, h, 2)
+    o, d = Oracle(w, h, ver), MobiclipDecoder(w, h, ver)
     ok, off, bgra = o.decode(data, 0)
     assert ok
     d.Data, d.Offset = data, 0
