@@ -81,7 +81,9 @@ typedef struct mobi_part {
 typedef struct mobi_coef {
     int16_t level;
     uint8_t pos;           /* bits 0-5 scan position; bits 6-7 4x4 sub-block inside a split 8x8 */
-    uint8_t blk;           /* bits 0-2 8x8 block (0-3 luma raster, 4 U, 5 V); bit 7: one 8x8 transform (else 4x4) */
+    uint8_t blk;           /* bits 0-2 8x8 block (0-3 luma raster, 4 U, 5 V); bits 3-4 macroblock index & 3 (the inter kernel
+                              pools the coefficients of four consecutive macroblocks and files each record by this tag);
+                              bit 6 last record of its transform unit; bit 7: one 8x8 transform (else 4x4) */
 } mobi_coef;                 /* 4 bytes */
 
 /* Intra operation, executed in stream order by one warp (MD:1759-1880, 2776-2902):

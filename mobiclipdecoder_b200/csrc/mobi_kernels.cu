@@ -745,9 +745,6 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
                         int4* z = reinterpret_cast<int4*>(&sm.u.coef[0][0]);
                         for (uint32_t q = lane; q < ns * 16u; q += 32u) z[q] = make_int4(0, 0, 0, 0);
                     }
-                    uint32_t st_i[RUN], n_i[RUN];
-#pragma unroll
-                    for (int i = 0; i < RUN; i++) { st_i[i] = __shfl_sync(0xffffffffu, d.z, l0 + i) - jmin; n_i[i] = __shfl_sync(0xffffffffu, n_coef, l0 + i); }
                     __syncwarp();
                     // ---- dequantise into the pool (MD:3424-3429) ----
                     uint32_t m8 = 0;
@@ -755,14 +752,15 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
                         const uint32_t j = j0 + (uint32_t)lane;
                         if (j < ntot) {
                             const uint32_t c = j0 == 0 ? ca : j0 == 32u ? cb : __ldg(cf + j);
-                            int own = -1;
-#pragma unroll
-                            for (int i = 0; i < RUN; i++) if (j - st_i[i] < n_i[i]) own = i;
-                            if (own >= 0) {
+                            // whose record: the parser tags every record with its macroblock's index & 3 (mobi_coef.blk bits 3-4), and
+                            // a run is four macroblocks aligned to four.  Records of intra macroblocks lying inside the range (k_intra's),
+                            // or naming a block their macroblock does not code, find no bit in the mask and are passed over.
+                            const uint32_t own = (c >> 27) & 3u, blk = (c >> 24) & 7u;
+                            const uint32_t mask = (bmp >> (8 * own)) & 63u;
+                            if ((mask >> blk) & 1u) {
                                 const int level = (int)(int16_t)(c & 0xFFFFu);
-                                const uint32_t pos = (c >> 16) & 63u, sub = (c >> 22) & 3u, blk = (c >> 24) & 7u, is8 = c >> 31;
+                                const uint32_t pos = (c >> 16) & 63u, sub = (c >> 22) & 3u, is8 = c >> 31;
                                 const uint32_t wq = __ldg(qtab + (is8 ? pos : 64u + (pos & 15u)));
-                                const uint32_t mask = (bmp >> (8 * own)) & 63u;
                                 const uint32_t slot = ((sbp >> (8 * own)) & 255u) + __popc(mask & ((1u << blk) - 1u));
                                 const uint32_t e = is8 ? (wq & 63u) : sub * 16u + (wq & 15u);
                                 sm.u.coef[slot][pool_word(slot, e >> 3, e & 7u)] = (int)(wq >> 8) * level;

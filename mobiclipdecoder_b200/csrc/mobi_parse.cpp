@@ -89,6 +89,7 @@ struct FrameParse {
     uint32_t max_ref = 0;
     uint32_t cur_deps = 0;
     int cur_mbx = 0, cur_mby = 0;
+    uint8_t own_tag = 0;   // (macroblock index & 3) << 3: rides in bits 3-4 of mobi_coef.blk (the inter kernel pools the coefficients of four macroblocks)
 
     int log2S;
     FrameParse(Parser& p, ParsedFrame& o) : P(p), out(o), S(p.S_), W((int)p.W_), H((int)p.H_), log2S(p.S_ == 256 ? 8 : p.S_ == 512 ? 9 : 10) {}
@@ -128,7 +129,7 @@ struct FrameParse {
         uint32_t win = b.win;
         int nb = b.nb, off = b.off;
         mobi_coef* dst = &out.coefs.v[out.coefs.n];
-        const uint8_t tag = (uint8_t)(blk | (n == 64 ? 0x80 : 0));
+        const uint8_t tag = (uint8_t)(blk | (n == 64 ? 0x80 : 0) | own_tag);
         // Refill (MD:2988-2996) without a data-dependent branch: whether the counter went negative is close to a coin flip
         // per coefficient, so the common case (a whole word is still available) does it arithmetically; the tail of the
         // buffer takes the literal path.
@@ -358,6 +359,7 @@ struct FrameParse {
         chroma(cbp6, mboff, mask);
     }
     void intra_mb(bool sub, int mboff) {
+        own_tag = (uint8_t)((out.mbs.size() & 3u) << 3);
         mobi_mb mb;
         uint32_t first_op = (uint32_t)out.ops.size(), first_coef = (uint32_t)out.coefs.size(), mask = 0;
         cur_deps = 0;
@@ -427,6 +429,7 @@ struct FrameParse {
     }
     void inter_mb(int mboff, int slot) {
         uint32_t first_part = (uint32_t)out.parts.size(), first_coef = (uint32_t)out.coefs.size(), mask = 0;
+        own_tag = (uint8_t)((out.mbs.size() & 3u) << 3);
         if (!pblock(3, 3, mboff, mboff, slot)) return;
         uint32_t cbp6 = tab(MOBI_CBP6_INTER, 64, b.uvar());  // loc_1161A0 MD:1818
         for (uint32_t m = cbp6 & 63u; m; m &= m - 1) blk8_inter((uint8_t)__builtin_ctz(m), mask);   // set bits only, ascending: no coin-flip branch per block

@@ -769,6 +769,8 @@ private:
             const uint32_t kind = mb.info & 3u, nsub = (mb.info >> 2) & 127u, nco = (mb.info >> 9) & 511u;
             if (kind > 1 || nsub > 64 || nco > 384) return set_err(MOBI_ERR_ARG, "packed frame: MB %u descriptor", m);
             if ((uint64_t)mb.first_coef + nco > h.n_coefs) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient range", m);
+            for (uint32_t k = 0; k < nco; k++)
+                if (((f.coefs[mb.first_coef + k].blk >> 3) & 3u) != (m & 3u)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient %u owner tag", m, k);
             if (kind == 1) {
                 if (nsub > 32) return set_err(MOBI_ERR_ARG, "packed frame: MB %u has more intra ops than any macroblock can (27)", m);
                 if ((uint64_t)mb.first_sub + nsub > h.n_ops) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op range", m);
