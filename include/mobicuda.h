@@ -8,7 +8,7 @@
  * handles, raw pointers, sizes; they return 0 on success and a negative mobi_status otherwise; no
  * exception crosses the boundary.  A handle is not thread-safe; distinct handles are independent.
  *
- * The P/Invoke binding a LibMobiclip maintainer would add is in csharp/MobiCuda.cs and described in
+ * The P/Invoke binding a LibMobiclip maintainer would add is in csharp/MobiclipDecoder.cs and described in
  * INTEGRATION.md; each export below cites the reference member it stands in for.
  */
 #ifndef MOBICUDA_H
@@ -133,6 +133,12 @@ int mobi_decode_frame(mobi_t* d, const uint8_t* data, int len, int* offset_inout
 
 /* Pre-parsed path (BASELINE config 2): reconstruct a frame from packed arrays in host memory. */
 int mobi_submit_packed(mobi_t* d, const mobi_packed_frame* f);
+
+/* The checks mobi_submit_packed applies to caller-supplied arrays before anything reaches the GPU, as a host-only call
+ * (no device needed): every index the kernels would use is range-checked (descriptor fields, op fields, partition
+ * geometry and tiling, vectors against the plane arrays, references against `pictures` = pictures in the ring, coefficient
+ * tags and the contiguity of the per-macroblock coefficient ranges).  err (optional) receives a diagnostic. */
+int mobi_packed_validate(uint32_t width, uint32_t height, int version, const mobi_packed_frame* f, int pictures, char* err, size_t err_len);
 
 /* Y[0] / UV[0] (MD:19-20).  strided = byte-identical to the reference arrays (Stride*H, Stride*H/2);
  * tight = cropped planar I420.  Host destinations; each call synchronises the decoder's stream. */

@@ -45,6 +45,7 @@ MOBICUDA_EXPORTS = {
     'mobi_destroy': (None, [C.c_void_p]),
     'mobi_decode_frame': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     'mobi_submit_packed': (C.c_int, [C.c_void_p, C.POINTER(PackedFrame)]),
+    'mobi_packed_validate': (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(PackedFrame), C.c_int, C.c_char_p, C.c_size_t]),
     'mobi_read_planes_strided': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'mobi_read_yuv': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mobi_read_bgra': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

@@ -111,9 +111,11 @@ int mobi_moc5_next(const uint8_t* data, size_t len, uint32_t* cursor, uint32_t* 
     const uint32_t bs = u32(data + offs);
     if (decode_offset) *decode_offset = offs + 8;
     if (block_size) *block_size = bs;
-    offs += 4 + (bs & ~1u);
-    while (offs % 4) offs++;
-    *cursor = offs;
+    // the next cursor in 64 bits: a crafted block size must not wrap it (the reference's int arithmetic ends in an exception)
+    uint64_t next = (uint64_t)offs + 4u + (uint64_t)(bs & ~1u);
+    next = (next + 3u) & ~(uint64_t)3u;
+    if (next <= offs || next > 0xFFFFFFFFull) return MOBI_ERR_BITSTREAM;
+    *cursor = (uint32_t)next;
     return 1;
 }
 

@@ -380,13 +380,13 @@ struct FrameParse {
         // the packed record holds 16-bit vectors; with that established, 32-bit arithmetic below cannot overflow
         if (dx < -32768 || dx > 32767 || dy < -32768 || dy > 32767) fail(MOBI_ERR_RANGE, "motion vector outside 16 bits");
         // CopyBlock reads (MD:418-456): luma, then both chroma planes at (dx>>1, dy>>1), half size
-        const int first = off + ((dy >> 1) << log2S) + (dx >> 1);
-        const int last = first + ((h - 1 + (dy & 1)) << log2S) + w - 1 + (dx & 1);
-        if (first < 0 || last >= (H << log2S)) fail(MOBI_ERR_RANGE, "motion vector reads outside the luma array");
+        const int first = off + (dy >> 1) * S + (dx >> 1);   // (multiplications: the vector components may be negative)
+        const int last = first + (h - 1 + (dy & 1)) * S + w - 1 + (dx & 1);
+        if (first < 0 || last >= H * S) fail(MOBI_ERR_RANGE, "motion vector reads outside the luma array");
         const int cdx = dx >> 1, cdy = dy >> 1;
-        const int cfirst = (off >> 1) + ((cdy >> 1) << log2S) + (cdx >> 1);
-        const int clast = cfirst + (S >> 1) + (((h >> 1) - 1 + (cdy & 1)) << log2S) + (w >> 1) - 1 + (cdx & 1);
-        if (cfirst < 0 || clast >= ((H << log2S) >> 1)) fail(MOBI_ERR_RANGE, "motion vector reads outside the chroma array");
+        const int cfirst = (off >> 1) + (cdy >> 1) * S + (cdx >> 1);
+        const int clast = cfirst + (S >> 1) + ((h >> 1) - 1 + (cdy & 1)) * S + (w >> 1) - 1 + (cdx & 1);
+        if (cfirst < 0 || clast >= H * S / 2) fail(MOBI_ERR_RANGE, "motion vector reads outside the chroma array");
         int rel = off - mboff, x = rel & (S - 1), y = rel >> log2S;
         mobi_part p;
         p.xy = (uint8_t)((x >> 1) | (y >> 1) << 4);

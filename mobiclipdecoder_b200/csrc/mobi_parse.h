@@ -48,6 +48,9 @@ public:
     uint32_t quantizer() const { return st_.quant; }
     uint32_t yuv_format() const { return st_.yuvfmt; }
     int pictures() const { return st_.decoded; }
+    // The ring is owned by the caller (the batch): it tells the parser how many pictures it holds before every parse, so
+    // that the two counts cannot drift apart (a reset of the ring, a step that failed after its parse succeeded).
+    void set_pictures(int n) { st_.decoded = n < 0 ? 0 : n > 6 ? 6 : n; }
     const std::string& error() const { return err_; }
     uint32_t width() const { return W_; }
     uint32_t height() const { return H_; }

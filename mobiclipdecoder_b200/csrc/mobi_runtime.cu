@@ -51,20 +51,25 @@ public:
         if (th_.empty() || n <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
         {
             std::lock_guard<std::mutex> l(m_);
-            fn_ = &fn; n_ = n; next_.store(0); active_ = (int)th_.size(); gen_++;
+            fn_ = &fn; n_ = n; next_.store(0); active_ = (int)th_.size(); gen_++; failed_.store(false);
         }
         cv_.notify_all();
         work();  // the caller helps
-        std::unique_lock<std::mutex> l(m_);
-        done_.wait(l, [this] { return active_ == 0; });
-        fn_ = nullptr;
+        {
+            std::unique_lock<std::mutex> l(m_);
+            done_.wait(l, [this] { return active_ == 0; });
+            fn_ = nullptr;
+        }
+        if (failed_.load()) throw std::bad_alloc();   // (the only thing the work items can throw; the C ABI maps it to MOBI_ERR_NOMEM)
     }
 private:
+    // No exception leaves a worker thread (std::terminate) or unwinds run() while workers still hold fn_: the first
+    // failure is remembered and rethrown by run() on the calling thread once every worker is done.
     void work() {
         for (;;) {
             int i = next_.fetch_add(1);
             if (i >= n_) break;
-            (*fn_)(i);
+            try { (*fn_)(i); } catch (...) { failed_.store(true); }
         }
     }
     void loop() {
@@ -88,6 +93,7 @@ private:
     std::condition_variable cv_, done_;
     const std::function<void(int)>* fn_ = nullptr;
     std::atomic<int> next_{0};
+    std::atomic<bool> failed_{false};
     int n_ = 0, active_ = 0;
     uint64_t gen_ = 0;
     bool stop_ = false;
@@ -128,6 +134,113 @@ struct OutSlot {
 };
 
 }  // namespace
+
+// Caller-supplied packed arrays are untrusted: everything the kernels index with is range-checked here (host only; also
+// exported as mobi_packed_validate so that it can be exercised without a device).
+struct PackedValidator {
+    Geom g_;
+    uint32_t H_, n_mb_;
+    std::string err_;
+    PackedValidator(const Geom& g, uint32_t h) : g_(g), H_(h), n_mb_((uint32_t)(g.mbw * g.mbh)) {}
+    int set_err(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err_ = buf;
+        return code;
+    }
+    int run(const mobi_packed_frame& f, int pictures) {
+        const mobi_frame_hdr& h = *f.hdr;
+        if (h.n_mb != n_mb_) return set_err(MOBI_ERR_ARG, "packed frame: n_mb %u, geometry needs %u", h.n_mb, n_mb_);
+        if ((h.n_mb && !f.mbs) || (h.n_parts && !f.parts) || (h.n_ops && !f.ops) || (h.n_coefs && !f.coefs) || (h.n_intra && !f.intra_list))
+            return set_err(MOBI_ERR_ARG, "packed frame: null array");
+        const int S = g_.S, H = (int)H_;
+        uint32_t n_intra = 0;
+        for (uint32_t m = 0; m < h.n_mb; m++) {
+            const mobi_mb& mb = f.mbs[m];
+            const uint32_t kind = mb.info & 3u, nsub = (mb.info >> 2) & 127u, nco = (mb.info >> 9) & 511u;
+            if (kind > 1 || nsub > 64 || nco > 384) return set_err(MOBI_ERR_ARG, "packed frame: MB %u descriptor", m);
+            if ((uint64_t)mb.first_coef + nco > h.n_coefs) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient range", m);
+            for (uint32_t k = 0; k < nco; k++)
+                if (((f.coefs[mb.first_coef + k].blk >> 3) & 3u) != (m & 3u)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient %u owner tag", m, k);
+            // the kernels pool the coefficient records of four consecutive macroblocks as ONE range of the array
+            if (m + 1 < h.n_mb && f.mbs[m + 1].first_coef != mb.first_coef + nco)
+                return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient ranges are not contiguous", m);
+            if (kind == 1) {
+                if (nsub > 32) return set_err(MOBI_ERR_ARG, "packed frame: MB %u has more intra ops than any macroblock can (27)", m);
+                if ((uint64_t)mb.first_sub + nsub > h.n_ops) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op range", m);
+                // every op field the intra kernels index shared memory with (tiles are 16x16 luma / 8x8 chroma + a halo)
+                const int mbx = (int)(m % (uint32_t)g_.mbw), mby = (int)(m / (uint32_t)g_.mbw);
+                const int mboff = mby * 16 * S + mbx * 16;
+                const uint32_t mask = (mb.info >> 18) & 63u;
+                for (uint32_t k = 0; k < nsub; k++) {
+                    const uint32_t op = f.ops[mb.first_sub + k];
+                    const uint32_t mode = op & 31u, plane = (op >> 6) & 3u, x4 = (op >> 8) & 3u, y4 = (op >> 10) & 3u;
+                    const bool res = (op >> 5) & 1u;
+                    if (mode > 20 || plane > 2) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op %u mode / plane", m, k);
+                    const uint32_t n4 = mode == 20 ? 4u : mode >= 10 ? 1u : 2u, cells = plane == 0 ? 4u : 2u;   // block and plane width in 4-pixel cells
+                    if (x4 + n4 > cells || y4 + n4 > cells) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op %u block outside the macroblock", m, k);
+                    if (plane != 0 && (mode == 8 || mode == 18)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op %u: chroma has no predictor 8 (MD:1866)", m, k);
+                    if (mode == 20 && res) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op %u: the 16x16 plane predictor carries no residual", m, k);
+                    const uint32_t blk = plane == 0 ? (y4 >> 1) * 2u + (x4 >> 1) : 3u + plane;
+                    if (res && !((mask >> blk) & 1u)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op %u names a residual its macroblock does not code", m, k);
+                    // what the parser's check_intra_reads rejects: a predictor reading above / left of the plane (MD:1893 etc. would throw)
+                    const int off = plane == 0 ? mboff + (int)y4 * 4 * S + (int)x4 * 4 : mboff / 2 + (plane == 2 ? S / 2 : 0) + (int)y4 * 4 * S + (int)x4 * 4;
+                    int lo = 0; bool reads = true;
+                    switch (mode) {
+                    case 0: case 8: case 2: case 10: case 18: case 12: case 20: lo = off - S; break;
+                    case 1: case 4: case 11: case 14: lo = off - 1; break;
+                    case 5: case 6: case 7: case 15: case 16: case 17: lo = off - S - 1; break;
+                    default: reads = false; break;
+                    }
+                    if (reads && (mode == 2 || mode == 12 || mode == 20) && off - 1 < lo) lo = off - 1;
+                    if (reads && lo < 0) return set_err(MOBI_ERR_RANGE, "packed frame: MB %u op %u predictor reads above/left of the picture", m, k);
+                }
+                if (mb.intra_rank != n_intra || mb.intra_rank >= h.n_intra || f.intra_list[mb.intra_rank] != m)   // ranks ascend in raster order
+                    return set_err(MOBI_ERR_ARG, "packed frame: MB %u intra rank", m);
+                n_intra++;
+                continue;
+            }
+            if (nsub == 0 || (uint64_t)mb.first_sub + nsub > h.n_parts) return set_err(MOBI_ERR_ARG, "packed frame: MB %u partition range", m);
+            if ((mb.info >> 28) & 1u) {  // inline copy of the single partition must agree with the record that is range-checked below
+                const mobi_part& p = f.parts[mb.first_sub];
+                const uint32_t want = ((uint32_t)p.mvx & 0x3FFFu) | ((uint32_t)p.mvy & 0x3FFFu) << 14 | (uint32_t)(p.shape >> 4) << 28;
+                if (nsub != 1 || mb.intra_rank != want || p.mvx < -8192 || p.mvx >= 8192 || p.mvy < -8192 || p.mvy >= 8192)
+                    return set_err(MOBI_ERR_ARG, "packed frame: MB %u inline partition", m);
+            }
+            const int mbx = (int)(m % (uint32_t)g_.mbw), mby = (int)(m / (uint32_t)g_.mbw);
+            uint64_t cover[4] = {0, 0, 0, 0};  // 16x16 luma pixels
+            for (uint32_t k = 0; k < nsub; k++) {
+                const mobi_part& p = f.parts[mb.first_sub + k];
+                const int x = (p.xy & 15) * 2, y = (p.xy >> 4) * 2, w = 2 << (p.shape & 3), hh = 2 << ((p.shape >> 2) & 3), ref = p.shape >> 4;
+                if (x + w > 16 || y + hh > 16) return set_err(MOBI_ERR_ARG, "packed frame: MB %u partition geometry", m);
+                if (ref < 1 || ref > 5 || ref > pictures) return set_err(MOBI_ERR_REFERENCE, "packed frame: MB %u references picture %d of %d", m, ref, pictures);
+                const long long offp = (long long)(mby * 16 + y) * S + mbx * 16 + x;
+                const int dx = p.mvx, dy = p.mvy;
+                const long long first = offp + (long long)(dy >> 1) * S + (dx >> 1);
+                const long long last = first + (long long)(hh - 1 + (dy & 1)) * S + w - 1 + (dx & 1);
+                if (first < 0 || last >= (long long)S * H) return set_err(MOBI_ERR_RANGE, "packed frame: MB %u luma vector", m);
+                const int cdx = dx >> 1, cdy = dy >> 1;
+                const long long cfirst = offp / 2 + (long long)(cdy >> 1) * S + (cdx >> 1);
+                const long long clast = cfirst + S / 2 + (long long)((hh >> 1) - 1 + (cdy & 1)) * S + (w >> 1) - 1 + (cdx & 1);
+                if (cfirst < 0 || clast >= (long long)S * H / 2) return set_err(MOBI_ERR_RANGE, "packed frame: MB %u chroma vector", m);
+                for (int yy = y; yy < y + hh; yy++) cover[yy >> 2] |= (uint64_t)((1u << w) - 1u) << ((yy & 3) * 16 + x);
+            }
+            for (int k = 0; k < 4; k++) if (cover[k] != ~0ull) return set_err(MOBI_ERR_ARG, "packed frame: MB %u partitions do not tile the macroblock", m);
+        }
+        if (n_intra != h.n_intra) return set_err(MOBI_ERR_ARG, "packed frame: intra count");
+        for (uint32_t k = 0; k < h.n_coefs; k++) {
+            const mobi_coef& c = f.coefs[k];
+            if ((c.blk & 7) > 5) return set_err(MOBI_ERR_ARG, "packed frame: coefficient %u block tag", k);
+            if (!(c.blk & 0x80) && (c.pos & 63) > 15) return set_err(MOBI_ERR_ARG, "packed frame: coefficient %u scan position", k);
+        }
+        for (int k = 0; k < 80; k++) {
+            const uint32_t idx = h.qtab[k] & 0xFF;
+            if (idx >= (k < 64 ? 64u : 16u)) return set_err(MOBI_ERR_ARG, "packed frame: scan table entry %d", k);
+        }
+        return MOBI_OK;
+    }
+
+};
 
 class Batch {
 public:
@@ -235,7 +348,7 @@ public:
         if (!data || !len || !offset) return set_err(MOBI_ERR_ARG, "null argument");
         if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
         rc_.assign(N_, MOBI_OK);
-        pool_.run(N_, [&](int i) { rc_[i] = parsers_[i]->parse(data[i], len[i], &offset[i], frames_[i]); });
+        pool_.run(N_, [&](int i) { rc_[i] = parse_one(i, data[i], len[i], &offset[i], count_[i]); });
         views_.resize(N_);
         int n_ok = 0, first_bad = -1;
         for (int i = 0; i < N_; i++) {
@@ -289,7 +402,7 @@ public:
         if (!data || !len || !offset) return set_err(MOBI_ERR_ARG, "null argument");
         if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
         rc_.assign(N_, MOBI_OK);
-        pool_.run(N_, [&](int i) { rc_[i] = parsers_[i]->parse(data[i], len[i], &offset[i], frames_[i]); });
+        pool_.run(N_, [&](int i) { rc_[i] = parse_one(i, data[i], len[i], &offset[i], staged_count_[i]); });
         views_.resize(N_);
         for (int i = 0; i < N_; i++) {
             if (rc_[i] != MOBI_OK) return set_err(rc_[i], "stream %d: %s", i, parsers_[i]->error().c_str());
@@ -537,6 +650,16 @@ public:
     }
 
 private:
+    // One stream's entropy parse.  The parser is told how many pictures the ring holds for this stream first (the ring is
+    // the authority: after mobi_batch_reset, or a step that failed after its parse succeeded, the parser's own count would
+    // be ahead), so a P-picture naming a picture the ring does not hold is MOBI_ERR_REFERENCE here, never a null reference
+    // on the device.  Nothing is thrown past this point on a worker thread.
+    int parse_one(int i, const uint8_t* data, int len, int* offset, int pictures) {
+        try {
+            parsers_[i]->set_pictures(pictures);
+            return parsers_[i]->parse(data, len, offset, frames_[i]);
+        } catch (...) { return MOBI_ERR_NOMEM; }
+    }
     bool ok(cudaError_t e, const char* what) {
         if (e == cudaSuccess) return true;
         set_err(MOBI_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -601,6 +724,11 @@ private:
             o.intra = p; p = align_up(p + sizeof(uint32_t) * h.n_intra, 256);
         }
         L.bytes = p;
+        for (int j = 0; j < L.n_jobs; j++) {   // a reference the ring does not hold must never reach the device (null plane / wrong picture)
+            const int s = L.job_stream[j];
+            if ((int)views_[s].hdr->max_ref > count[s])
+                return set_err(MOBI_ERR_REFERENCE, "stream %d: picture references ring index %u but only %d pictures are decoded", s, views_[s].hdr->max_ref, count[s]);
+        }
         int rc = ensure_arena(a, L.bytes);
         if (rc != MOBI_OK) return rc;
         DevJob* jobs = reinterpret_cast<DevJob*>(a.h + L.jobs_off);
@@ -756,67 +884,11 @@ private:
         return MOBI_OK;
     }
 
-    // Caller-supplied packed arrays are untrusted: everything the kernels index with is range-checked here.
     int validate(const mobi_packed_frame& f, int pictures) {
-        const mobi_frame_hdr& h = *f.hdr;
-        if (h.n_mb != n_mb_) return set_err(MOBI_ERR_ARG, "packed frame: n_mb %u, geometry needs %u", h.n_mb, n_mb_);
-        if ((h.n_mb && !f.mbs) || (h.n_parts && !f.parts) || (h.n_ops && !f.ops) || (h.n_coefs && !f.coefs) || (h.n_intra && !f.intra_list))
-            return set_err(MOBI_ERR_ARG, "packed frame: null array");
-        const int S = g_.S, H = (int)H_;
-        uint32_t n_intra = 0;
-        for (uint32_t m = 0; m < h.n_mb; m++) {
-            const mobi_mb& mb = f.mbs[m];
-            const uint32_t kind = mb.info & 3u, nsub = (mb.info >> 2) & 127u, nco = (mb.info >> 9) & 511u;
-            if (kind > 1 || nsub > 64 || nco > 384) return set_err(MOBI_ERR_ARG, "packed frame: MB %u descriptor", m);
-            if ((uint64_t)mb.first_coef + nco > h.n_coefs) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient range", m);
-            for (uint32_t k = 0; k < nco; k++)
-                if (((f.coefs[mb.first_coef + k].blk >> 3) & 3u) != (m & 3u)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient %u owner tag", m, k);
-            if (kind == 1) {
-                if (nsub > 32) return set_err(MOBI_ERR_ARG, "packed frame: MB %u has more intra ops than any macroblock can (27)", m);
-                if ((uint64_t)mb.first_sub + nsub > h.n_ops) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op range", m);
-                if (mb.intra_rank != n_intra || mb.intra_rank >= h.n_intra || f.intra_list[mb.intra_rank] != m)   // ranks ascend in raster order
-                    return set_err(MOBI_ERR_ARG, "packed frame: MB %u intra rank", m);
-                n_intra++;
-                continue;
-            }
-            if (nsub == 0 || (uint64_t)mb.first_sub + nsub > h.n_parts) return set_err(MOBI_ERR_ARG, "packed frame: MB %u partition range", m);
-            if ((mb.info >> 28) & 1u) {  // inline copy of the single partition must agree with the record that is range-checked below
-                const mobi_part& p = f.parts[mb.first_sub];
-                const uint32_t want = ((uint32_t)p.mvx & 0x3FFFu) | ((uint32_t)p.mvy & 0x3FFFu) << 14 | (uint32_t)(p.shape >> 4) << 28;
-                if (nsub != 1 || mb.intra_rank != want || p.mvx < -8192 || p.mvx >= 8192 || p.mvy < -8192 || p.mvy >= 8192)
-                    return set_err(MOBI_ERR_ARG, "packed frame: MB %u inline partition", m);
-            }
-            const int mbx = (int)(m % (uint32_t)g_.mbw), mby = (int)(m / (uint32_t)g_.mbw);
-            uint64_t cover[4] = {0, 0, 0, 0};  // 16x16 luma pixels
-            for (uint32_t k = 0; k < nsub; k++) {
-                const mobi_part& p = f.parts[mb.first_sub + k];
-                const int x = (p.xy & 15) * 2, y = (p.xy >> 4) * 2, w = 2 << (p.shape & 3), hh = 2 << ((p.shape >> 2) & 3), ref = p.shape >> 4;
-                if (x + w > 16 || y + hh > 16) return set_err(MOBI_ERR_ARG, "packed frame: MB %u partition geometry", m);
-                if (ref < 1 || ref > 5 || ref > pictures) return set_err(MOBI_ERR_REFERENCE, "packed frame: MB %u references picture %d of %d", m, ref, pictures);
-                const long long offp = (long long)(mby * 16 + y) * S + mbx * 16 + x;
-                const int dx = p.mvx, dy = p.mvy;
-                const long long first = offp + (long long)(dy >> 1) * S + (dx >> 1);
-                const long long last = first + (long long)(hh - 1 + (dy & 1)) * S + w - 1 + (dx & 1);
-                if (first < 0 || last >= (long long)S * H) return set_err(MOBI_ERR_RANGE, "packed frame: MB %u luma vector", m);
-                const int cdx = dx >> 1, cdy = dy >> 1;
-                const long long cfirst = offp / 2 + (long long)(cdy >> 1) * S + (cdx >> 1);
-                const long long clast = cfirst + S / 2 + (long long)((hh >> 1) - 1 + (cdy & 1)) * S + (w >> 1) - 1 + (cdx & 1);
-                if (cfirst < 0 || clast >= (long long)S * H / 2) return set_err(MOBI_ERR_RANGE, "packed frame: MB %u chroma vector", m);
-                for (int yy = y; yy < y + hh; yy++) cover[yy >> 2] |= (uint64_t)((1u << w) - 1u) << ((yy & 3) * 16 + x);
-            }
-            for (int k = 0; k < 4; k++) if (cover[k] != ~0ull) return set_err(MOBI_ERR_ARG, "packed frame: MB %u partitions do not tile the macroblock", m);
-        }
-        if (n_intra != h.n_intra) return set_err(MOBI_ERR_ARG, "packed frame: intra count");
-        for (uint32_t k = 0; k < h.n_coefs; k++) {
-            const mobi_coef& c = f.coefs[k];
-            if ((c.blk & 7) > 5) return set_err(MOBI_ERR_ARG, "packed frame: coefficient %u block tag", k);
-            if (!(c.blk & 0x80) && (c.pos & 63) > 15) return set_err(MOBI_ERR_ARG, "packed frame: coefficient %u scan position", k);
-        }
-        for (int k = 0; k < 80; k++) {
-            const uint32_t idx = h.qtab[k] & 0xFF;
-            if (idx >= (k < 64 ? 64u : 16u)) return set_err(MOBI_ERR_ARG, "packed frame: scan table entry %d", k);
-        }
-        return MOBI_OK;
+        PackedValidator v(g_, H_);
+        const int rc = v.run(f, pictures);
+        if (rc != MOBI_OK) err_ = v.err_;
+        return rc;
     }
 
     uint32_t W_, H_;
@@ -875,6 +947,23 @@ int check_geometry(uint32_t w, uint32_t h, int version) {
 }  // namespace
 
 extern "C" {
+
+int mobi_packed_validate(uint32_t width, uint32_t height, int version, const mobi_packed_frame* f, int pictures, char* err, size_t err_len) {
+    if (err && err_len) err[0] = 0;
+    int rc = check_geometry(width, height, version);
+    if (rc != MOBI_OK) return rc;
+    if (!f || !f->hdr) return MOBI_ERR_ARG;
+    mobi::Geom g;
+    g.W = (int)width; g.H = (int)height; g.S = mobi::stride_for(width); g.version = version;
+    g.log2S = g.S == 256 ? 8 : g.S == 512 ? 9 : 10;
+    g.mbw = (int)width / 16; g.mbh = (int)height / 16;
+    try {
+        mobi::PackedValidator v(g, height);
+        rc = v.run(*f, pictures);
+        if (rc != MOBI_OK && err && err_len) { strncpy(err, v.err_.c_str(), err_len - 1); err[err_len - 1] = 0; }
+        return rc;
+    } catch (...) { return MOBI_ERR_NOMEM; }
+}
 
 int mobi_create(uint32_t width, uint32_t height, int version, int device, mobi_t** out) {
     if (!out) return MOBI_ERR_ARG;
