@@ -321,18 +321,30 @@ def main():
     batch.replay(Wm, K)
     kt = batch.kernel_times()
     batch.set_kernel_timing(False)
-    inter_bytes = (768 + 16) * d['inter_mbs'] + 8 * d['parts'] + 4 * d['inter_coefs']
+    fused = os.environ.get('MOBI_INTER_KERNEL') != 'split'   # MC + residual in one kernel (the default) or as k_mc + k_res
+    inter_name = ('k_inter_v3' if os.environ.get('MOBI_INTER_KERNEL') == 'v3' else 'k_inter_chunk') if fused else 'k_mc'
+    # MC = reference read once + reconstruction written + descriptor + 8 B per partition; the residual side
+    # information (4 B per coefficient) belongs to whichever kernel consumes it
+    mc_bytes = (768 + 16) * d['inter_mbs'] + 8 * d['parts']
+    res_bytes = 16 * d['inter_mbs'] + 4 * d['inter_coefs']
+    inter_bytes = mc_bytes + (4 * d['inter_coefs'] if fused else 0)
     intra_bytes = (384 + 32) * d['intra_mbs'] + 4 * d['ops'] + 4 * (d['coefs'] - d['inter_coefs'])
     n_il = max(1, kt['inter_launches'])
     inter_ms = kt['inter_ms'] / n_il
+    res_ms = kt['res_ms'] / max(1, kt['res_launches'])
     achieved = (inter_bytes / n_il) / (inter_ms * 1e-3) / 1e9 if inter_ms > 0 else 0.0
-    inter_name = 'k_inter' if os.environ.get('MOBI_INTER_KERNEL') == 'warp' else 'k_inter_chunk'   # which inter kernel the library runs
     roofline = {'bound': 'hbm', 'kernel': inter_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': NCU_TRAFFIC.get(inter_name), 'algorithmic_bytes_per_launch': inter_bytes / n_il, 'launch_ms': inter_ms,
                 'launches_timed': kt['inter_launches'], 'peak_source': peak_src,
-                'step_ms_by_kernel': {inter_name: kt['inter_ms'] / K, 'k_intra_p_pictures': kt['intra_ms'] / K,
+                'step_ms_by_kernel': {inter_name: kt['inter_ms'] / K, 'k_res': kt['res_ms'] / K, 'k_intra_p_pictures': kt['intra_ms'] / K,
                                       'k_intra_i_pictures_side_stream': kt['key_ms'] / K},
                 'intra_algorithmic_bytes_per_step': intra_bytes / K}
+    if not fused and res_ms > 0:
+        # the whole inter path (k_mc + k_res) against the fused accounting of earlier rounds, and k_res on its own side information
+        roofline['inter_path'] = {'kernels': 'k_mc + k_res', 'launch_ms': inter_ms + res_ms, 'algorithmic_bytes_per_launch': (mc_bytes + 4 * d['inter_coefs']) / n_il,
+                                  'achieved': ((mc_bytes + 4 * d['inter_coefs']) / n_il) / ((inter_ms + res_ms) * 1e-3) / 1e9}
+        roofline['inter_path']['frac'] = roofline['inter_path']['achieved'] / peak
+        roofline['k_res'] = {'launch_ms': res_ms, 'side_info_bytes_per_launch': res_bytes / n_il}
 
     # ---- e2e leg: host bytes -> parse -> H2D -> reconstruct -> convert -> D2H (pinned) -------------------------
     # Headline output is what the reference call returns, the BGRA bitmap (MD:260-323); the I420 variant (decoded

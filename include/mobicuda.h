@@ -61,6 +61,8 @@ typedef struct mobi_mb {
                               bits 9-17 n_coefs (<= 384); bits 18-23 mask of 8x8 blocks holding >= 1 coefficient;
                               bits 24-27 (intra) neighbouring macroblocks whose pixels the predictors read:
                               1 left (m-1), 2 top-left (m-mbw-1), 4 top (m-mbw), 8 top-right (m-mbw+1);
+                              bits 24-27 and 29-30 (inter) which of the coded blocks 0-3 / 4-5 are transformed as one 8x8
+                              (the rest as 4x4 units): the same fact as bit 7 of their coefficient records' blk;
                               bit 28 (inter) the single partition is also stored inline in intra_rank */
     uint32_t first_sub;    /* index of the first mobi_part (inter) or mobi_op (intra) */
     uint32_t first_coef;   /* index of the first mobi_coef */
@@ -211,9 +213,10 @@ int mobi_batch_get_stats(const mobi_batch_t* b, mobi_batch_stats* st);
  * by CUDA events on the batch's stream.  mobi_batch_get_kernel_times synchronises, returns the summed durations
  * (milliseconds) and launch counts since the last call, and clears them. */
 int mobi_batch_set_kernel_timing(mobi_batch_t* b, int enabled);
-/* index 0: k_inter; 1: k_intra over the intra macroblocks of P-pictures; 2: k_intra over I-pictures (runs on a second
- * CUDA stream, concurrently with the other two) */
-int mobi_batch_get_kernel_times(mobi_batch_t* b, double ms[3], uint64_t launches[3]);
+/* index 0: k_mc (motion compensation of the inter macroblocks); 1: k_intra over the intra macroblocks of P-pictures; 2: k_intra
+ * over I-pictures (runs on a second CUDA stream, concurrently with the others); 3: k_res (dequantisation + inverse transforms
+ * of the inter macroblocks, added in place) */
+int mobi_batch_get_kernel_times(mobi_batch_t* b, double ms[4], uint64_t launches[4]);
 void mobi_batch_clear_stats(mobi_batch_t* b);
 
 int mobicuda_abi_version(void);

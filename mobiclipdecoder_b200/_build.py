@@ -50,7 +50,7 @@ def build_mobicuda(force=False, verbose=False):
     os.makedirs(LIB, exist_ok=True)
     out = os.path.join(LIB, 'libmobicuda.so')
     srcs = [os.path.join(CSRC, f) for f in ('mobi_kernels.cu', 'mobi_runtime.cu', 'mobi_parse.cpp', 'mobi_demux.cpp')]
-    deps = srcs + [os.path.join(CSRC, f) for f in ('mobi_kernels.h', 'mobi_parse.h', 'mobi_tables.h')] + [os.path.join(ROOT, 'include', 'mobicuda.h'), os.path.join(ROOT, 'include', 'mobidemux.h')]
+    deps = srcs + [os.path.join(CSRC, f) for f in ('mobi_kernels.h', 'mobi_inter_v3.cuh', 'mobi_inter_split.cuh', 'mobi_parse.h', 'mobi_tables.h')] + [os.path.join(ROOT, 'include', 'mobicuda.h'), os.path.join(ROOT, 'include', 'mobidemux.h')]
     if force or _newer(out, deps):
         log = _run([nvcc_path()] + NVCC_FLAGS + ['-shared', '-o', out] + srcs, verbose)
         with open(os.path.join(LIB, 'ptxas.log'), 'w') as f:

@@ -23,7 +23,6 @@
 namespace mobi {
 namespace {
 
-constexpr int INTER_WARPS = 8;
 // ids of the set bits of a 6-bit coded-block mask, one nibble each, lowest first (slot order of the coefficient buffers)
 __constant__ uint32_t c_blklist[64];
 constexpr int INTRA_WARPS = 4;
@@ -127,35 +126,20 @@ __device__ __forceinline__ uint32_t addsat4(uint32_t px, int r0, int r1, int r2,
 // inter macroblocks
 // ------------------------------------------------------------------------------------------------
 // Reference pixels arrive by TMA: the whole ring is one rank-3 u8 tensor (Stride, 1.5*H, pictures), so a macroblock's
-// 16x16+halo luma window lies inside one 32x17 box and each chroma window inside one 32x9 box, fetched by one lane
-// straight into shared memory (TMA wants the innermost start coordinate 16-byte aligned -- an unaligned start raises
-// "illegal instruction" -- so boxes start at the window's column rounded down to 16 and lanes apply the remainder
-// when they read shared memory).  This takes the gathers off the LSU path, which is what bounds a load-per-lane formulation (every
-// warp-wide load touches 16 cache lines).  TMA zero-fills outside the tensor whereas the reference addresses its planes
-// flat (a column < 0 or >= Stride wraps into the neighbouring row), so windows that leave the row horizontally, and
-// macroblocks split into more than TMA_MAXP leaves, take the load-per-lane path instead.
-constexpr int TMA_MAXP = 2;
-constexpr uint32_t TMA_BYTES_L = 32 * 17, TMA_BYTES_C = 32 * 9;
-
-// Per-warp shared memory.  The reference windows are dead once the prediction is in registers, so the coefficient
-// blocks of the CODED 8x8 blocks (compacted: slot = rank of the block among the coded ones) reuse their space.
-struct InterSmem {
-    union {
-        struct {
-            uint8_t ref_l[TMA_MAXP][640];      // 32x17 luma boxes (128-byte aligned for TMA)
-            uint8_t ref_c[TMA_MAXP][2][384];   // 32x9 U and V boxes
-        } in;
-        int32_t coef[6][64];
-    } u;
-    uint8_t tile[384];     // prediction + residual: luma 16 rows x 16, then U 8x8, V 8x8
-    uint8_t map[64];       // 2x2-granular partition map of a split macroblock
-    uint2 parts[64];       // its leaf records
-    uint64_t bar;
-    uint8_t pad[56];
-};
-static_assert(sizeof(InterSmem) % 128 == 0, "per-warp shared memory must keep TMA destinations 128-byte aligned");
+// 16x16+halo luma window lies inside one 32x17 box, and (rank-4 view, each row split into its U and V halves) both chroma
+// windows inside one 32x2x9 box, fetched by one lane straight into shared memory (TMA wants the innermost start coordinate
+// 16-byte aligned -- an unaligned start raises "illegal instruction" -- so boxes start at the window's column rounded down
+// to 16 and lanes apply the remainder when they read shared memory).  This takes the gathers off the LSU path, which is
+// what bounds a load-per-lane formulation (every warp-wide load touches 16 cache lines).  TMA zero-fills outside the
+// tensor whereas the reference addresses its planes flat (a column < 0 or >= Stride wraps into the neighbouring row), so
+// windows that leave their pixel row take a load-per-lane path instead.
+constexpr uint32_t TMA_BYTES_L = 32 * 17;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
@@ -206,244 +190,45 @@ __device__ __forceinline__ uint32_t tile_px(const uint8_t* t, int pitch, int pha
     return (((a >> 1) + (t[1] >> 1)) >> 1) + (((t[pitch] >> 1) + (t[pitch + 1] >> 1)) >> 1);
 }
 
+// ------------------------------------------------------------------------------------------------
+// L2 prefetch of a chunk's reference region
+// ------------------------------------------------------------------------------------------------
+// EXPERIMENT (MOBI_INTER_EXP=8), measured and not adopted.  What bounds the inter path is the rate at which the boxes' rows
+// come out of the memory system (tools/probe/tma_rate.cu: a 32x17 box costs 29 SM-cycles when its rows hit L2 and 70-115 when
+// they come from DRAM; the kernels run at 68 cycles per box with half of their sectors missing L2): every box row is its own
+// sector or two, rows lie Stride bytes apart.  Most leaves point into the previous picture close to where they sit, so the
+// idea was to ask L2, before a warp issues a chunk's boxes, for the whole region of picture 1 the chunk's windows can be
+// expected in, as full 128-byte lines.  Result on the bench mix: DRAM reads 414 -> 517 MB per launch, L2 hit rate unchanged
+// (52 %), kernel 0.263 -> 0.301 ms: the lines a chunk asks for are mostly the ones its neighbours' boxes already brought, and
+// what misses are the 20 % of leaves that point into OTHER pictures, which no such region covers.
 template <int LOG2S>
-__global__ void __launch_bounds__(INTER_WARPS * 32, 7) k_inter(const DevJob* __restrict__ jobs, int mbw, uint32_t mbw_magic, int H,
-                                                           const __grid_constant__ CUtensorMap tm_l, const __grid_constant__ CUtensorMap tm_c) {
-    __shared__ __align__(128) InterSmem s_all[INTER_WARPS];
+__device__ __forceinline__ void prefetch_rows(const uint8_t* plane, int x_lo, int x_hi, int y_lo, int y_hi, int y_max, int lane) {
     constexpr int S = 1 << LOG2S;
-    const DevJob& J = jobs[blockIdx.y];
-    if (J.n_intra == J.n_mb) return;  // I-picture: nothing for this kernel
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t mb = blockIdx.x * INTER_WARPS + warp;
-    if (mb >= J.n_mb) return;
-    const uint4 d = __ldg(reinterpret_cast<const uint4*>(J.mbs + mb));
-    if (d.x & 3u) return;  // intra MB: k_intra's job
-    InterSmem& sm = s_all[warp];
-    const uint32_t bar = smem_u32(&sm.bar);
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // init visible to the async (TMA) proxy; CTA scope: no L1 invalidate
+    x_lo = max(x_lo, 0) & ~127; x_hi = min(x_hi, S);
+    y_lo = max(y_lo, 0); y_hi = min(y_hi, y_max);
+    const int lines = (x_hi - x_lo + 127) >> 7, n = lines * (y_hi - y_lo);
+    if (lines <= 0) return;
+    for (int i = lane; i < n; i += 32) {
+        const int r = i / lines, c = i - r * lines;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(plane + ((size_t)(y_lo + r) << LOG2S) + x_lo + c * 128));
     }
-    const int n_parts = (int)((d.x >> 2) & 127u), n_coef = (int)((d.x >> 9) & 511u);
-    const uint32_t blkmask = (d.x >> 18) & 63u;
-    const int mby = (int)__umulhi(mb, mbw_magic), mbx = (int)mb - mby * mbw;   // exact for mb < 2^26 (magic = ceil(2^32 / mbw))
-    const size_t ysz = (size_t)S * H;
-    const int yoff = ((mby * 16) << LOG2S) + mbx * 16, coff = yoff >> 1;
-    const int lrow = lane >> 1, lhalf = lane & 1;
-    const int cpl = lane >> 4, crow = (lane >> 1) & 7;
-    const int ypix = yoff + (lrow << LOG2S) + lhalf * 8;                           // this lane's luma pixels
-    const int cpix = coff + (cpl ? (S >> 1) : 0) + (crow << LOG2S) + lhalf * 4;    // this lane's chroma pixels
-    // coefficient records do not depend on the prediction: fetch the first 32 now
-    const uint32_t* cf = reinterpret_cast<const uint32_t*>(J.coefs) + d.z;
-    uint32_t c_first = 0;
-    if (lane < n_coef) c_first = __ldg(cf + lane);
-    uint32_t y0, y1, c0;
-
-    // ---- leaf records: inline (unsplit macroblock), or loaded ----
-    PartV p0, p1;
-    p1.mvx = p1.mvy = 0; p1.ref = 1;
-    if (n_parts == 1 && (d.x & (1u << 28))) {  // the partition travels inside the descriptor: no dependent load
-        p0.mvx = ((int)(d.w << 18)) >> 18; p0.mvy = ((int)(d.w << 4)) >> 18; p0.ref = (int)(d.w >> 28);
-    } else {
-        const mobi_part* parts = J.parts + d.y;
-        for (int i = lane; i < n_parts; i += 32) sm.parts[i] = __ldg(reinterpret_cast<const uint2*>(parts + i));
-        __syncwarp();
-        { const uint2 w = sm.parts[0]; p0 = part_of(w.x, w.y); }
-        if (n_parts > 1) { const uint2 w = sm.parts[1]; p1 = part_of(w.x, w.y); }
+}
+// Macroblocks first .. first + count - 1 (raster order, may run over the end of a macroblock row) of a W-pixel-wide picture:
+// luma rows -MARGIN .. 16 + MARGIN around each row of macroblocks, the U and V rows that go with them.
+template <int LOG2S>
+__device__ __forceinline__ void prefetch_chunk_region(const uint8_t* ref, int H, int mbw, int first_mbx, int first_mby, int count, int lane) {
+    constexpr int S = 1 << LOG2S, MARGIN = 9;
+    if (!ref) return;
+    const uint8_t* const chroma = ref + ((size_t)H << LOG2S);
+    int mbx = first_mbx, mby = first_mby;
+    while (count > 0) {
+        const int n = min(count, mbw - mbx);
+        const int x0 = mbx * 16 - MARGIN, x1 = (mbx + n) * 16 + MARGIN, y0 = mby * 16 - MARGIN, y1 = mby * 16 + 16 + MARGIN;
+        prefetch_rows<LOG2S>(ref, x0, x1, y0, y1, H, lane);
+        prefetch_rows<LOG2S>(chroma, x0 >> 1, (x1 + 1) >> 1, y0 >> 1, (y1 + 1) >> 1, H >> 1, lane);                        // U
+        prefetch_rows<LOG2S>(chroma + (S >> 1), x0 >> 1, (x1 + 1) >> 1, y0 >> 1, (y1 + 1) >> 1, H >> 1, lane);             // V
+        count -= n; mbx = 0; mby++;
     }
-    // Can the windows be fetched as TMA boxes?  Only when every column they need lies inside its own pixel row.
-    bool tma = n_parts <= TMA_MAXP;
-    {
-        const int x0 = mbx * 16 + (p0.mvx >> 1), cx0 = mbx * 8 + (p0.mvx >> 2);
-        tma = tma && x0 >= 0 && x0 + 17 <= S && cx0 >= 0 && cx0 + 9 <= (S >> 1);
-        if (n_parts == 2) {
-            const int x1 = mbx * 16 + (p1.mvx >> 1), cx1 = mbx * 8 + (p1.mvx >> 2);
-            tma = tma && x1 >= 0 && x1 + 17 <= S && cx1 >= 0 && cx1 + 9 <= (S >> 1);
-        }
-    }
-    if (tma) {
-        __syncwarp();  // barrier initialised
-        if (lane == 0) {
-            const uint32_t bytes = (uint32_t)n_parts * (TMA_BYTES_L + 2 * TMA_BYTES_C);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-            for (int i = 0; i < n_parts; i++) {
-                const PartV p = i ? p1 : p0;
-                const int pic = (int)J.ref_pic[p.ref - 1];
-                const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                const int xl = mbx * 16 + (p.mvx >> 1), xc = mbx * 8 + (cx >> 1);
-                tma_load_3d(smem_u32(sm.u.in.ref_l[i]), &tm_l, xl & ~15, mby * 16 + (p.mvy >> 1), pic, bar);
-                tma_load_3d(smem_u32(sm.u.in.ref_c[i][0]), &tm_c, xc & ~15, H + mby * 8 + (cy >> 1), pic, bar);
-                tma_load_3d(smem_u32(sm.u.in.ref_c[i][1]), &tm_c, (S >> 1) + (xc & ~15), H + mby * 8 + (cy >> 1), pic, bar);
-            }
-        }
-    }
-
-    // ---- which leaf covers each of this lane's 2x2 cells (split macroblocks) ----
-    uint32_t ml = 0, mc = 0;
-    if (n_parts > 1) {
-        // Partition map at 2x2-pixel granularity (leaves go down to 2x2, MD:1726), built cell-parallel: lane l owns
-        // cells 2l and 2l+1 of the 8x8 cell grid and tests them against every leaf rectangle.
-        const int cy2 = lane >> 2, cx2 = (lane & 3) * 2;
-        uint32_t i0 = 0, i1 = 0;
-        for (int i = 0; i < n_parts; i++) {
-            const uint32_t w = sm.parts[i].x;
-            const int x2 = w & 15, y2 = (w >> 4) & 15, cw = 1 << ((w >> 8) & 3), ch = 1 << ((w >> 10) & 3);
-            const bool rowin = (unsigned)(cy2 - y2) < (unsigned)ch;
-            if (rowin && (unsigned)(cx2 - x2) < (unsigned)cw) i0 = (uint32_t)i;
-            if (rowin && (unsigned)(cx2 + 1 - x2) < (unsigned)cw) i1 = (uint32_t)i;
-        }
-        reinterpret_cast<uint16_t*>(sm.map)[lane] = (uint16_t)(i0 | i1 << 8);
-        __syncwarp();
-        ml = *reinterpret_cast<const uint32_t*>(sm.map + (lrow >> 1) * 8 + lhalf * 4);
-        mc = *reinterpret_cast<const uint32_t*>(sm.map + crow * 8 + lhalf * 4);
-    }
-    const bool l_uni = ml == (ml & 255u) * 0x01010101u, c_uni = mc == (mc & 255u) * 0x01010101u;
-
-    if (tma) {
-        uint32_t done;
-        do {
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
-        } while (!done);
-        if (l_uni) {
-            const int i = (int)(ml & 255u);
-            const PartV p = i ? p1 : p0;
-            tile_row8(sm.u.in.ref_l[i], (uint32_t)(lrow * 32 + ((mbx * 16 + (p.mvx >> 1)) & 15) + lhalf * 8), (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
-        } else {
-            uint32_t o[2] = {0, 0};
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int i = (int)((ml >> (8 * c)) & 255u);
-                const PartV p = i ? p1 : p0;
-                const uint8_t* t = sm.u.in.ref_l[i] + lrow * 32 + ((mbx * 16 + (p.mvx >> 1)) & 15) + lhalf * 8 + 2 * c;
-                const int ph = (p.mvx & 1) | ((p.mvy & 1) << 1);
-                o[c >> 1] |= (tile_px(t, 32, ph) | tile_px(t + 1, 32, ph) << 8) << (16 * (c & 1));
-            }
-            y0 = o[0]; y1 = o[1];
-        }
-        if (c_uni) {
-            const int i = (int)(mc & 255u);
-            const PartV p = i ? p1 : p0;
-            const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-            c0 = tile_row4(sm.u.in.ref_c[i][cpl], (uint32_t)(crow * 32 + ((mbx * 8 + (cx >> 1)) & 15) + lhalf * 4), (cx & 1) | ((cy & 1) << 1));
-        } else {
-            c0 = 0;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int i = (int)((mc >> (8 * c)) & 255u);
-                const PartV p = i ? p1 : p0;
-                const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                c0 |= tile_px(sm.u.in.ref_c[i][cpl] + crow * 32 + ((mbx * 8 + (cx >> 1)) & 15) + lhalf * 4 + c, 32, (cx & 1) | ((cy & 1) << 1)) << (8 * c);
-            }
-        }
-        __syncwarp();  // all lanes are done with the windows before the coefficient blocks overwrite them
-    } else {
-        auto leaf = [&](uint32_t idx) { if (n_parts == 1) return p0; const uint2 w = sm.parts[idx]; return part_of(w.x, w.y); };
-        if (l_uni) {
-            const PartV p = leaf(ml & 255u);
-            mc_row8(J.ref[p.ref - 1] + ypix + ((p.mvy >> 1) << LOG2S) + (p.mvx >> 1), S, (p.mvx & 1) | ((p.mvy & 1) << 1), y0, y1);
-        } else {
-            uint32_t o[2] = {0, 0};
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const PartV p = leaf((ml >> (8 * c)) & 255u);
-                const uint8_t* s = J.ref[p.ref - 1] + ypix + 2 * c + ((p.mvy >> 1) << LOG2S) + (p.mvx >> 1);
-                const int ph = (p.mvx & 1) | ((p.mvy & 1) << 1);
-                const uint32_t v = mc_px(s, S, ph) | mc_px(s + 1, S, ph) << 8;
-                o[c >> 1] |= v << (16 * (c & 1));
-            }
-            y0 = o[0]; y1 = o[1];
-        }
-        if (c_uni) {
-            const PartV p = leaf(mc & 255u);
-            const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-            c0 = mc_row4(J.ref[p.ref - 1] + ysz + cpix + ((cy >> 1) << LOG2S) + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1));
-        } else {
-            c0 = 0;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const PartV p = leaf((mc >> (8 * c)) & 255u);
-                const int cx = p.mvx >> 1, cy = p.mvy >> 1;
-                c0 |= mc_px(J.ref[p.ref - 1] + ysz + cpix + c + ((cy >> 1) << LOG2S) + (cx >> 1), S, (cx & 1) | ((cy & 1) << 1)) << (8 * c);
-            }
-        }
-    }
-
-    if (n_coef) {
-        // ---- dequantise into the compacted coefficient blocks (MD:3424-3429) ----
-        const int nblk = __popc(blkmask);
-        {
-            int4* z = reinterpret_cast<int4*>(&sm.u.coef[0][0]) + lane;
-            const int nz = nblk * 16 - lane;   // <= 96: at most three rounds
-            if (nz > 0) z[0] = make_int4(0, 0, 0, 0);
-            if (nz > 32) z[32] = make_int4(0, 0, 0, 0);
-            if (nz > 64) z[64] = make_int4(0, 0, 0, 0);
-        }
-        *reinterpret_cast<uint2*>(sm.tile + lrow * 16 + lhalf * 8) = make_uint2(y0, y1);
-        *reinterpret_cast<uint32_t*>(sm.tile + 256 + cpl * 64 + crow * 8 + lhalf * 4) = c0;
-        __syncwarp();
-        const uint32_t* __restrict__ qtab = J.hdr->qtab;
-        uint32_t m8 = 0;
-        for (int j = lane; j < n_coef; j += 32) {
-            const uint32_t c = j < 32 ? c_first : __ldg(cf + j);
-            const int level = (int)(int16_t)(c & 0xFFFFu);
-            const uint32_t pos = (c >> 16) & 63u, sub = (c >> 22) & 3u, blk = (c >> 24) & 7u, is8 = c >> 31;
-            const uint32_t w = __ldg(qtab + (is8 ? pos : 64u + (pos & 15u)));
-            const uint32_t slot = __popc(blkmask & ((1u << blk) - 1u));
-            sm.u.coef[slot][is8 ? (w & 63u) : sub * 16u + (w & 15u)] = (int)(w >> 8) * level;
-            m8 |= is8 << blk;
-        }
-        m8 = __reduce_or_sync(0xffffffffu, m8);
-        const uint32_t list = c_blklist[blkmask];   // ids of the coded blocks, one nibble each, in slot order
-        __syncwarp();
-
-        // ---- inverse transforms: eight lanes per coded block (one row each), four blocks per pass ----
-        const int g = lane >> 3, r = lane & 7, i4 = r & 3, s0 = (r >> 2) * 2;
-        for (int base = 0; base < nblk; base += 4) {
-            const int slot = base + g;
-            const bool has = slot < nblk;
-            const int b = (int)((list >> (4 * slot)) & 7u);
-            const bool is8 = (m8 >> b) & 1u;
-            int32_t* B = sm.u.coef[has ? slot : 0];
-            int32_t in[8], v[8];
-            if (has) {
-                const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r : s0 * 16 + 4 * i4));
-                const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r + 4 : (s0 + 1) * 16 + 4 * i4));
-                in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
-                if (is8) { if (r == 0) in[0] += 32; bfly8(in, v); }
-                else { if (i4 == 0) { in[0] += 32; in[4] += 32; } bfly4(in, v); bfly4(in + 4, v + 4); }
-            }
-            __syncwarp();
-            if (has) {
-                if (is8) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) B[8 * k + r] = v[k];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) { B[s0 * 16 + 4 * k + i4] = v[k]; B[(s0 + 1) * 16 + 4 * k + i4] = v[4 + k]; }
-                }
-            }
-            __syncwarp();
-            if (has) {
-                const int4 lo = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r : s0 * 16 + 4 * i4));
-                const int4 hi = *reinterpret_cast<const int4*>(B + (is8 ? 8 * r + 4 : (s0 + 1) * 16 + 4 * i4));
-                in[0] = lo.x; in[1] = lo.y; in[2] = lo.z; in[3] = lo.w; in[4] = hi.x; in[5] = hi.y; in[6] = hi.z; in[7] = hi.w;
-                if (is8) bfly8(in, v); else { bfly4(in, v); bfly4(in + 4, v + 4); }
-                // either way the lane now holds the residuals of row r, columns 0..7 of block b: add onto the prediction
-                uint8_t* t = b < 4 ? sm.tile + ((b >> 1) * 8 + r) * 16 + (b & 1) * 8 : sm.tile + 256 + (b - 4) * 64 + r * 8;
-                uint2 px = *reinterpret_cast<uint2*>(t);
-                px.x = addsat4(px.x, v[0], v[1], v[2], v[3]);
-                px.y = addsat4(px.y, v[4], v[5], v[6], v[7]);
-                *reinterpret_cast<uint2*>(t) = px;
-            }
-            __syncwarp();
-        }
-        const uint2 yy = *reinterpret_cast<const uint2*>(sm.tile + lrow * 16 + lhalf * 8);
-        y0 = yy.x; y1 = yy.y;
-        c0 = *reinterpret_cast<const uint32_t*>(sm.tile + 256 + cpl * 64 + crow * 8 + lhalf * 4);
-    }
-
-    *reinterpret_cast<uint2*>(J.dst + ypix) = make_uint2(y0, y1);
-    *reinterpret_cast<uint32_t*>(J.dst + ysz + cpix) = c0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -531,7 +316,7 @@ constexpr uint32_t MCW_INTER = 1u << 24, MCW_BOX = 1u << 25, MCW_TWO = 1u << 26,
 template <int LOG2S>
 __global__ void __launch_bounds__(CH_WARPS * 32, 7)
 k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, uint32_t cpp_magic, int mbw, uint32_t mbw_magic, int H,
-              uint32_t* __restrict__ ticket, uint32_t ticket_base,
+              uint32_t* __restrict__ ticket, uint32_t ticket_base, uint32_t prefetch_on,
               const __grid_constant__ CUtensorMap tm_l, const __grid_constant__ CUtensorMap tm_c4) {
     constexpr int RUN = 4;
     using Smem = RunSmem<RUN>;
@@ -563,6 +348,10 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
         if (J.n_intra != n_mb) {   // an I-picture has nothing for this kernel
             // ---- lane-parallel set-up: lanes l and l + 16 look after macroblock mbc + l ----
             const uint32_t mbc = chunk * CH_MBS;
+            if (prefetch_on) {
+                const int fy = (int)__umulhi(mbc, mbw_magic);
+                prefetch_chunk_region<LOG2S>(J.ref[0], H, mbw, (int)mbc - fy * mbw, fy, (int)min((uint32_t)CH_MBS, n_mb - mbc), lane);
+            }
             const bool in = mbc + k16 < n_mb;
             const uint32_t mbk = in ? mbc + k16 : n_mb - 1;
             const uint4 d = __ldg(reinterpret_cast<const uint4*>(J.mbs + mbk));
@@ -860,6 +649,9 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
         t = __shfl_sync(0xffffffffu, t_next, 0) - ticket_base;
     }
 }
+
+#include "mobi_inter_v3.cuh"
+#include "mobi_inter_split.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // intra macroblocks
@@ -1377,32 +1169,78 @@ cudaError_t init_kernel_tables() {
     return cudaMemcpyToSymbol(c_blklist, lut, sizeof lut);
 }
 
-// k_inter_chunk unless MOBI_INTER_KERNEL=warp asks for k_inter (one warp per macroblock; kept for comparison).
-static bool inter_kernel_is_warp() {
-    static const bool warp = [] { const char* e = getenv("MOBI_INTER_KERNEL"); return e && !strcmp(e, "warp"); }();
-    return warp;
+// The inter path.  Three formulations exist, all bit-exact (tests/test_gpu_parity.py runs each) and all within 5 % of each other
+// on the bench mix -- they share their bound, the rate at which TMA delivers small boxes at a 50 % L2 hit rate (DESIGN.md 4,
+// tools/probe/tma_rate.cu) -- so the default is the fastest, last round's fused kernel:
+//   (default)                  k_inter_chunk: MC + residual fused, runs of 4 macroblocks, 4 box slots per run
+//   MOBI_INTER_KERNEL=v3       k_inter_v3 (mobi_inter_v3.cuh): box slots in rounds, per-leaf eligibility, conflict-free coefficient
+//                              pool in visiting order, DC-only blocks without a transform; MOBI_INTER_CHUNK=8 (8-macroblock
+//                              chunks) and MOBI_INTER_CTAS=6 / 8 (CTAs per SM the layout is sized for; default 7)
+//   MOBI_INTER_KERNEL=split    k_mc + k_res (mobi_inter_split.cuh): motion compensation and residual as two kernels at 36-40
+//                              warps per SM, macroblocks of more than two leaves by boxes too; gives the MC and the IDCT kernel
+//                              their own times (bench.py reports them)
+static int inter_kernel_choice() {   // -1: k_mc + k_res; 0: k_inter_chunk; else k_inter_v3 with CTAs per SM * 2 + (8-macroblock chunks ? 1 : 0)
+    static const int c = [] {
+        const char* e = getenv("MOBI_INTER_KERNEL");
+        const char* ch = getenv("MOBI_INTER_CHUNK");
+        const char* ct = getenv("MOBI_INTER_CTAS");
+        if (e && !strcmp(e, "split")) return -1;
+        if (!e || strcmp(e, "v3")) return 0;
+        const int ctas = ct && (!strcmp(ct, "6") || !strcmp(ct, "8")) ? atoi(ct) : 7;
+        return ctas * 2 + ((ch && !strcmp(ch, "8")) ? 1 : 0);
+    }();
+    return c;
 }
+const char* inter_kernel_name() { const int c = inter_kernel_choice(); return c < 0 ? "k_mc+k_res" : c == 0 ? "k_inter_chunk" : "k_inter_v3"; }
 
-cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, const CUtensorMap& tm_c4,
-                         int sm_count, uint32_t* ticket, uint32_t ticket_base, uint32_t* tickets_drawn, cudaStream_t st) {
-    *tickets_drawn = 0;
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const InterMaps& tm, int sm_count, uint32_t* tickets, uint32_t* ticket_base,
+                         cudaStream_t st, cudaEvent_t* between) {
     if (n_jobs <= 0) return cudaSuccess;
     const uint32_t magic = (uint32_t)((0x100000000ull + (uint64_t)g.mbw - 1) / (uint64_t)g.mbw);
-    if (!inter_kernel_is_warp()) {
-        const uint32_t cpp = (uint32_t)((g.mbw * g.mbh + CH_MBS - 1) / CH_MBS), n_chunks = cpp * (uint32_t)n_jobs;
-        const uint32_t cpp_magic = (uint32_t)((0x100000000ull + (uint64_t)cpp - 1) / (uint64_t)cpp);
-        uint32_t ctas = (uint32_t)sm_count * 7u;
-        if (ctas > (n_chunks + CH_WARPS - 1) / CH_WARPS) ctas = (n_chunks + CH_WARPS - 1) / CH_WARPS;
-        if (g.log2S == 8) k_inter_chunk<8><<<ctas, CH_WARPS * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, ticket, ticket_base, tm_l, tm_c4);
-        else if (g.log2S == 9) k_inter_chunk<9><<<ctas, CH_WARPS * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, ticket, ticket_base, tm_l, tm_c4);
-        else k_inter_chunk<10><<<ctas, CH_WARPS * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, ticket, ticket_base, tm_l, tm_c4);
-        *tickets_drawn = n_chunks + ctas * CH_WARPS;   // every warp draws exactly one ticket past the end
+    const int choice = inter_kernel_choice();
+    static const uint32_t exp_flags = [] { const char* e = getenv("MOBI_INTER_EXP"); return e ? (uint32_t)atoi(e) : 0u; }();   // timing experiments: 1 no residual (wrong pixels), 2 v3 without the multi-leaf box path, 4 k_mc without chroma boxes (wrong pixels), 8 L2 prefetch of the chunk's region
+    const uint32_t chunk_mbs = (choice > 0 && (choice & 1)) ? 8u : 16u;
+    const uint32_t cpp = ((uint32_t)(g.mbw * g.mbh) + chunk_mbs - 1) / chunk_mbs, n_chunks = cpp * (uint32_t)n_jobs;
+    const uint32_t cpp_magic = (uint32_t)((0x100000000ull + (uint64_t)cpp - 1) / (uint64_t)cpp);
+    if (choice < 0) {
+        uint32_t ctas = (uint32_t)sm_count * (uint32_t)MC_CTAS, rctas = (uint32_t)sm_count * (uint32_t)RES_CTAS;
+        if (ctas > (n_chunks + MC_WARPS - 1) / MC_WARPS) ctas = (n_chunks + MC_WARPS - 1) / MC_WARPS;
+        if (rctas > (n_chunks + RES_WARPS - 1) / RES_WARPS) rctas = (n_chunks + RES_WARPS - 1) / RES_WARPS;
+#define MOBI_MC(L) k_mc<L><<<ctas, MC_WARPS * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, tm.ring_rows, tickets, ticket_base[0], exp_flags, tm.l2, tm.c3)
+#define MOBI_RES(L) k_res<L><<<rctas, RES_WARPS * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, tickets + 16, ticket_base[1])
+        if (g.log2S == 8) MOBI_MC(8); else if (g.log2S == 9) MOBI_MC(9); else MOBI_MC(10);
+        ticket_base[0] += n_chunks + ctas * MC_WARPS;   // every warp draws exactly one ticket past the end
+        if (between) { cudaEventRecord(between[0], st); cudaEventRecord(between[1], st); }
+        if (!(exp_flags & 1u)) {
+            if (g.log2S == 8) MOBI_RES(8); else if (g.log2S == 9) MOBI_RES(9); else MOBI_RES(10);
+            ticket_base[1] += n_chunks + rctas * RES_WARPS;
+        }
+#undef MOBI_MC
+#undef MOBI_RES
         return cudaGetLastError();
     }
-    dim3 grid((unsigned)((g.mbw * g.mbh + INTER_WARPS - 1) / INTER_WARPS), (unsigned)n_jobs);
-    if (g.log2S == 8) k_inter<8><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
-    else if (g.log2S == 9) k_inter<9><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
-    else k_inter<10><<<grid, INTER_WARPS * 32, 0, st>>>(jobs, g.mbw, magic, g.H, tm_l, tm_c);
+    const uint32_t warps = choice == 0 ? CH_WARPS : V3_WARPS;
+    uint32_t ctas = (uint32_t)sm_count * (choice == 0 ? 7u : (uint32_t)(choice >> 1));
+    if (ctas > (n_chunks + warps - 1) / warps) ctas = (n_chunks + warps - 1) / warps;
+#define MOBI_LAUNCH(K) K<<<ctas, warps * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, tickets, ticket_base[0], (exp_flags & 8u) ? 1u : 0u, tm.l3, tm.c4)
+#define MOBI_LAUNCH3(K) K<<<ctas, warps * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, tm.ring_rows, tickets, ticket_base[0], exp_flags, tm.l2, tm.c3)
+#define MOBI_BY_STRIDE(C, T) do { if (g.log2S == 8) MOBI_LAUNCH3((k_inter_v3<8, C, T>)); else if (g.log2S == 9) MOBI_LAUNCH3((k_inter_v3<9, C, T>)); else MOBI_LAUNCH3((k_inter_v3<10, C, T>)); } while (0)
+    switch (choice) {
+    case 0:
+        if (g.log2S == 8) MOBI_LAUNCH(k_inter_chunk<8>); else if (g.log2S == 9) MOBI_LAUNCH(k_inter_chunk<9>); else MOBI_LAUNCH(k_inter_chunk<10>);
+        break;
+    case 12: MOBI_BY_STRIDE(16, 6); break;
+    case 13: MOBI_BY_STRIDE(8, 6); break;
+    case 14: MOBI_BY_STRIDE(16, 7); break;
+    case 15: MOBI_BY_STRIDE(8, 7); break;
+    case 16: MOBI_BY_STRIDE(16, 8); break;
+    default: MOBI_BY_STRIDE(8, 8); break;
+    }
+#undef MOBI_BY_STRIDE
+#undef MOBI_LAUNCH3
+#undef MOBI_LAUNCH
+    ticket_base[0] += n_chunks + ctas * warps;   // every warp draws exactly one ticket past the end
+    if (between) { cudaEventRecord(between[0], st); cudaEventRecord(between[1], st); }
     return cudaGetLastError();
 }
 

@@ -34,14 +34,20 @@ struct Geom {
 
 // Constant tables of the kernels; once per device, before the first launch.
 cudaError_t init_kernel_tables();
-// Inter macroblocks of every job: MC from the ring + dequant/IDCT/add/clip.  One warp per MB.
-// tm_l / tm_c: the ring as a rank-3 u8 tensor (Stride, 1.5*H, pictures) with boxes 32x17x1 (luma windows) and 32x9x1 (chroma windows).
-// tm_c4: the ring as a rank-4 u8 tensor (Stride/2, 2, 1.5*H, pictures) -- each row split into its U and V halves -- with
-// box 32x2x9x1: the U and the V window of a leaf in one fetch.
-// The persistent variant hands out chunks of 16 macroblocks through *ticket (monotonic, like launch_intra's): the next
-// launch's ticket_base is ticket_base + *tickets_drawn.
-cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const CUtensorMap& tm_l, const CUtensorMap& tm_c, const CUtensorMap& tm_c4,
-                         int sm_count, uint32_t* ticket, uint32_t ticket_base, uint32_t* tickets_drawn, cudaStream_t st);
+// The ring of pictures as TMA tensors.  A picture is ring_rows rows of Stride bytes (luma rows, chroma rows, padding), pictures
+// follow each other without a gap, so the whole ring is ONE rank-2 u8 tensor:
+//   l2: (Stride, rows of all pictures), box 32x17 -- a luma window;
+//   c3: (Stride/2, 2, rows of all pictures) -- each row split into its U and V halves -- box 32x2x9: the U and the V window of a leaf;
+//   l3 / c4: the same with the picture as a coordinate of its own (what k_inter_chunk takes).
+struct InterMaps { CUtensorMap l2, c3, l3, c4; int ring_rows; };
+// Inter macroblocks of every job: motion compensation from the ring (k_mc), then dequantisation + inverse transforms added in
+// place (k_res); persistent warps drawing chunks of 16 macroblocks through tickets[0] (k_mc) and tickets[16] (k_res), both
+// monotonic like launch_intra's -- ticket_base[0..1] are advanced by what this launch draws.  between[0..1] (optional) are
+// recorded back to back between the two kernels (per-kernel timing: end of k_mc, start of k_res).
+cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const InterMaps& tm, int sm_count, uint32_t* tickets, uint32_t* ticket_base,
+                         cudaStream_t st, cudaEvent_t* between);
+// Which inter kernel launch_inter runs (environment: MOBI_INTER_KERNEL), for reports.
+const char* inter_kernel_name();
 // Intra macroblocks (I-frames and intra MBs of P-frames) as a dependency wavefront.  One warp per MB; work is handed
 // out through an atomic ticket in dependency-depth order so that a waiting warp's dependencies are always running.
 // *warps_launched receives the number of warps started: each draws exactly one ticket past n_work, so the

@@ -89,6 +89,7 @@ struct FrameParse {
     uint32_t max_ref = 0;
     uint32_t cur_deps = 0;
     int cur_mbx = 0, cur_mby = 0;
+    uint32_t cur_m8 = 0;   // coded blocks of the macroblock in hand that are transformed as one 8x8
     uint8_t own_tag = 0;   // (macroblock index & 3) << 3: rides in bits 3-4 of mobi_coef.blk (the inter kernel pools the coefficients of four macroblocks)
 
     int log2S;
@@ -203,6 +204,7 @@ struct FrameParse {
         out.coefs.n = (size_t)(dst - out.coefs.v.data());
         b.win = win; b.nb = nb; b.off = off;
         blkmask_any |= 1u << (blk & 7);
+        if (n == 64) cur_m8 |= 1u << (blk & 7);
     }
 
     // ---- intra -----------------------------------------------------------------------------
@@ -430,12 +432,13 @@ struct FrameParse {
     void inter_mb(int mboff, int slot) {
         uint32_t first_part = (uint32_t)out.parts.size(), first_coef = (uint32_t)out.coefs.size(), mask = 0;
         own_tag = (uint8_t)((out.mbs.size() & 3u) << 3);
+        cur_m8 = 0;
         if (!pblock(3, 3, mboff, mboff, slot)) return;
         uint32_t cbp6 = tab(MOBI_CBP6_INTER, 64, b.uvar());  // loc_1161A0 MD:1818
         for (uint32_t m = cbp6 & 63u; m; m &= m - 1) blk8_inter((uint8_t)__builtin_ctz(m), mask);   // set bits only, ascending: no coin-flip branch per block
         mobi_mb mb;
         uint32_t np = (uint32_t)out.parts.size() - first_part, nco = (uint32_t)out.coefs.size() - first_coef;
-        mb.info = 0u | np << 2 | nco << 9 | mask << 18;
+        mb.info = 0u | np << 2 | nco << 9 | mask << 18 | (cur_m8 & 15u) << 24 | (cur_m8 >> 4) << 29;   // bits 24-27, 29-30: which coded blocks are 8x8-transformed
         mb.first_sub = first_part; mb.first_coef = first_coef; mb.intra_rank = 0;
         if (np == 1) {  // an unsplit macroblock carries its vector inside the descriptor (saves the device a dependent load)
             const mobi_part& p = out.parts[first_part];

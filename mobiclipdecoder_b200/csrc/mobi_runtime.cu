@@ -160,8 +160,18 @@ struct PackedValidator {
             const uint32_t kind = mb.info & 3u, nsub = (mb.info >> 2) & 127u, nco = (mb.info >> 9) & 511u;
             if (kind > 1 || nsub > 64 || nco > 384) return set_err(MOBI_ERR_ARG, "packed frame: MB %u descriptor", m);
             if ((uint64_t)mb.first_coef + nco > h.n_coefs) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient range", m);
-            for (uint32_t k = 0; k < nco; k++)
-                if (((f.coefs[mb.first_coef + k].blk >> 3) & 3u) != (m & 3u)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient %u owner tag", m, k);
+            // inter macroblocks: which coded blocks are 8x8-transformed (info bits 24-27, 29-30) -- the inter kernel lays the
+            // coefficient pool out by this mask, so every record must agree with it and name a block the macroblock codes
+            const uint32_t bmask = (mb.info >> 18) & 63u, m8 = kind == 0 ? ((mb.info >> 24) & 15u) | ((mb.info >> 29) & 3u) << 4 : 0u;
+            if (kind == 0 && (m8 & ~bmask)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u 8x8-transform mask names blocks that are not coded", m);
+            for (uint32_t k = 0; k < nco; k++) {
+                const mobi_coef& c = f.coefs[mb.first_coef + k];
+                if (((c.blk >> 3) & 3u) != (m & 3u)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient %u owner tag", m, k);
+                if (kind == 0 && (c.blk & 7u) < 6u) {
+                    if (!((bmask >> (c.blk & 7u)) & 1u)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient %u names a block the macroblock does not code", m, k);
+                    if (((m8 >> (c.blk & 7u)) & 1u) != (uint32_t)(c.blk >> 7)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient %u disagrees with the 8x8-transform mask", m, k);
+                }
+            }
             // the kernels pool the coefficient records of four consecutive macroblocks as ONE range of the array
             if (m + 1 < h.n_mb && f.mbs[m + 1].first_coef != mb.first_coef + nco)
                 return set_err(MOBI_ERR_ARG, "packed frame: MB %u coefficient ranges are not contiguous", m);
@@ -251,7 +261,7 @@ public:
         g_.mbw = (int)w / 16; g_.mbh = (int)h / 16;
         n_mb_ = (uint32_t)(g_.mbw * g_.mbh);
         ysz_ = (size_t)g_.S * h;
-        pic_ = align_up(ysz_ * 3 / 2 + 256, 256);
+        pic_ = align_up(ysz_ * 3 / 2 + 256, (size_t)g_.S);   // whole rows: the ring is also addressed as one tensor of rows
         for (int i = 0; i < n_streams; i++) parsers_.emplace_back(new Parser(w, h, version));
         frames_.resize(n_streams);
         count_.assign(n_streams, 0);
@@ -270,7 +280,7 @@ public:
             if (out_h_) cudaFreeHost(out_h_);
             if (ptr_d_) cudaFree(ptr_d_);
             if (ptr_h_) cudaFreeHost(ptr_h_);
-            for (int w = 0; w < 3; w++) for (cudaEvent_t e : ev_[w]) cudaEventDestroy(e);
+            for (int w = 0; w < 4; w++) for (cudaEvent_t e : ev_[w]) cudaEventDestroy(e);
             if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
             if (copy_) { cudaStreamSynchronize(copy_); cudaStreamDestroy(copy_); }
             if (fork_) cudaEventDestroy(fork_);
@@ -312,8 +322,7 @@ public:
         if (!ok(cudaStreamSynchronize(stream_), "init sync")) return MOBI_ERR_CUDA;
         return make_tensor_maps();
     }
-    // The ring as one rank-3 u8 tensor (Stride, 1.5*H, pictures): a picture's chroma rows follow its luma rows at the
-    // same pitch, pictures are pic_ bytes apart.  cuTensorMapEncodeTiled is reached through the runtime so that the
+    // The ring as TMA tensors (InterMaps, mobi_kernels.h).  cuTensorMapEncodeTiled is reached through the runtime so that the
     // library does not link libcuda.
     int make_tensor_maps() {
         void* fn = nullptr;
@@ -321,23 +330,39 @@ public:
         if (!ok(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres), "cudaGetDriverEntryPoint") || !fn || qres != cudaDriverEntryPointSuccess)
             return set_err(MOBI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
         auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-        const cuuint64_t dims[3] = {(cuuint64_t)g_.S, (cuuint64_t)H_ * 3 / 2, (cuuint64_t)N_ * RING};
-        const cuuint64_t strides[2] = {(cuuint64_t)g_.S, (cuuint64_t)pic_};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        const cuuint32_t box_l[3] = {32, 17, 1}, box_c[3] = {32, 9, 1};
-        CUresult r = encode(&tm_l_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ring_, dims, strides, box_l, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r == CUDA_SUCCESS)
-            r = encode(&tm_c_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ring_, dims, strides, box_c, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const cuuint64_t S = (cuuint64_t)g_.S, rows = (cuuint64_t)(pic_ / S), pics = (cuuint64_t)N_ * RING;
+        tm_.ring_rows = (int)rows;
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        // MOBI_TMA_L2PROMO = 64 / 128 / 256: L2 promotion of the boxes' misses (experiments; default none)
+        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_NONE;
+        if (const char* e = getenv("MOBI_TMA_L2PROMO")) {
+            const int v = atoi(e);
+            promo = v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo;
+        }
+        auto enc = [&](CUtensorMap* m, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* bx) {
+            return encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, ring_, dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        };
+        CUresult r;
+        {
+            const cuuint64_t dims[2] = {S, rows * pics}, strides[1] = {S};
+            const cuuint32_t bx[2] = {32, 17};
+            r = enc(&tm_.l2, 2, dims, strides, bx);
+        }
         if (r == CUDA_SUCCESS) {
-            // each row as (U half, V half): one 32x2x9 box holds both chroma windows of a leaf
-            const cuuint64_t dims4[4] = {(cuuint64_t)g_.S / 2, 2, (cuuint64_t)H_ * 3 / 2, (cuuint64_t)N_ * RING};
-            const cuuint64_t strides4[3] = {(cuuint64_t)g_.S / 2, (cuuint64_t)g_.S, (cuuint64_t)pic_};
-            const cuuint32_t estr4[4] = {1, 1, 1, 1};
-            const cuuint32_t box_c4[4] = {32, 2, 9, 1};
-            r = encode(&tm_c4_, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, ring_, dims4, strides4, box_c4, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            const cuuint64_t dims[3] = {S / 2, 2, rows * pics}, strides[2] = {S / 2, S};
+            const cuuint32_t bx[3] = {32, 2, 9};
+            r = enc(&tm_.c3, 3, dims, strides, bx);
+        }
+        if (r == CUDA_SUCCESS) {
+            const cuuint64_t dims[3] = {S, (cuuint64_t)H_ * 3 / 2, pics}, strides[2] = {S, (cuuint64_t)pic_};
+            const cuuint32_t bx[3] = {32, 17, 1};
+            r = enc(&tm_.l3, 3, dims, strides, bx);
+        }
+        if (r == CUDA_SUCCESS) {
+            const cuuint64_t dims[4] = {S / 2, 2, (cuuint64_t)H_ * 3 / 2, pics}, strides[3] = {S / 2, S, (cuuint64_t)pic_};
+            const cuuint32_t bx[4] = {32, 2, 9, 1};
+            r = enc(&tm_.c4, 4, dims, strides, bx);
         }
         if (r != CUDA_SUCCESS) return set_err(MOBI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
         return MOBI_OK;
@@ -605,17 +630,22 @@ public:
 
     // ---- per-kernel timing (roofline accounting) ---------------------------------------------------
     void set_timing(bool on) { timing_ = on; }
-    void tick(int which, cudaStream_t st) {
+    cudaEvent_t fresh_event() {
         cudaEvent_t e;
         if (ev_free_.empty()) cudaEventCreate(&e); else { e = ev_free_.back(); ev_free_.pop_back(); }
+        return e;
+    }
+    void tick(int which, cudaStream_t st) {
+        cudaEvent_t e = fresh_event();
         cudaEventRecord(e, st);
         ev_[which].push_back(e);
     }
-    // which: 0 k_inter, 1 k_intra over P-pictures, 2 k_intra over I-pictures (side stream)
+    // which: 0 the inter kernel (k_mc; the fused kernel where one is selected), 1 k_intra over P-pictures, 2 k_intra over
+    // I-pictures (side stream), 3 k_res
     int kernel_times(double* ms_out, uint64_t* n_out) {
         int rc = sync();
         if (rc != MOBI_OK) return rc;
-        for (int w = 0; w < 3; w++) {
+        for (int w = 0; w < 4; w++) {
             double ms = 0; uint64_t n = 0;
             for (size_t i = 0; i + 1 < ev_[w].size(); i += 2) {
                 float t = 0;
@@ -852,23 +882,23 @@ private:
             if (!ok(cudaEventRecord(fork_, stream_), "cudaEventRecord")) return MOBI_ERR_CUDA;
             if (!ok(cudaStreamWaitEvent(side_, fork_, 0), "cudaStreamWaitEvent")) return MOBI_ERR_CUDA;
             if (timing_) tick(2, side_);
-            if (!ok(launch_intra_key(jobs, work, d + L.key_off, L.n_key_jobs, g_, ticket_ + 32, side_), "k_intra_key")) return MOBI_ERR_CUDA;
+            if (!ok(launch_intra_key(jobs, work, d + L.key_off, L.n_key_jobs, g_, ticket_ + 48, side_), "k_intra_key")) return MOBI_ERR_CUDA;
             if (timing_) tick(2, side_);
             stats_.launches++;
             if (!ok(cudaEventRecord(join_, side_), "cudaEventRecord")) return MOBI_ERR_CUDA;
             key_resident_ += (uint32_t)L.n_key_jobs;
             if (L.n_inter_jobs) {   // let the few large I-picture CTAs settle before the flood of small k_inter CTAs
-                if (!ok(launch_gate(ticket_ + 32, key_resident_, stream_), "k_gate")) return MOBI_ERR_CUDA;
+                if (!ok(launch_gate(ticket_ + 48, key_resident_, stream_), "k_gate")) return MOBI_ERR_CUDA;
                 stats_.launches++;
             }
         }
         if (L.n_inter_jobs) {
-            if (timing_) tick(0, stream_);
-            uint32_t drawn = 0;
-            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_l_, tm_c_, tm_c4_, sm_count_, ticket_ + 16, inter_ticket_base_, &drawn, stream_), "k_inter")) return MOBI_ERR_CUDA;
-            inter_ticket_base_ += drawn;
-            if (timing_) tick(0, stream_);
-            stats_.launches++;
+            // k_mc then k_res: with timing on, the event between them closes the first kernel's bracket and opens the second's
+            cudaEvent_t mid[2] = {nullptr, nullptr};
+            if (timing_) { tick(0, stream_); mid[0] = fresh_event(); mid[1] = fresh_event(); }
+            if (!ok(launch_inter(jobs, L.n_jobs, g_, tm_, sm_count_, ticket_ + 16, inter_ticket_base_, stream_, timing_ ? mid : nullptr), "k_mc / k_res")) return MOBI_ERR_CUDA;
+            if (timing_) { ev_[0].push_back(mid[0]); ev_[3].push_back(mid[1]); tick(3, stream_); }
+            stats_.launches += 2;
         }
         if (L.n_work_p) {
             uint32_t warps = 0;
@@ -907,8 +937,8 @@ private:
     uint8_t* ring_ = nullptr;
     uint32_t* flags_ = nullptr;
     uint32_t* ticket_ = nullptr;
-    uint32_t ticket_base_ = 0, inter_ticket_base_ = 0, stamp_ = 0, key_resident_ = 0;   // ticket_[0]: work tickets of k_intra; ticket_[16]: chunk tickets of k_inter_chunk; ticket_[32]: resident I-picture CTAs
-    CUtensorMap tm_l_, tm_c_, tm_c4_;
+    uint32_t ticket_base_ = 0, inter_ticket_base_[2] = {0, 0}, stamp_ = 0, key_resident_ = 0;   // ticket_[0]: work tickets of k_intra; ticket_[16], [32]: chunk tickets of k_mc, k_res; ticket_[48]: resident I-picture CTAs
+    InterMaps tm_;
     cudaStream_t side_ = nullptr, copy_ = nullptr;
     cudaEvent_t fork_ = nullptr, join_ = nullptr;
     std::vector<std::vector<uint16_t>> depth_;
@@ -922,7 +952,7 @@ private:
     const uint8_t** ptr_d_ = nullptr;
     const uint8_t** ptr_h_ = nullptr;
     bool timing_ = false;
-    std::vector<cudaEvent_t> ev_[3], ev_free_;
+    std::vector<cudaEvent_t> ev_[4], ev_free_;
     OutSlot slot_[2];
     int slot_head_ = 0, slots_used_ = 0;
     mobi_batch_stats stats_{};
@@ -1049,7 +1079,7 @@ int mobi_batch_set_kernel_timing(mobi_batch_t* b, int enabled) {
     b->b.set_timing(enabled != 0);
     return MOBI_OK;
 }
-int mobi_batch_get_kernel_times(mobi_batch_t* b, double ms[3], uint64_t launches[3]) {
+int mobi_batch_get_kernel_times(mobi_batch_t* b, double ms[4], uint64_t launches[4]) {
     return b ? b->b.kernel_times(ms, launches) : MOBI_ERR_ARG;
 }
 

@@ -346,10 +346,11 @@ class MobiBatch:
 
     def kernel_times(self):
         """Per-kernel device time since the last call (synchronises):
-        {'inter_ms', 'inter_launches', 'intra_ms', 'intra_launches', 'key_ms', 'key_launches'}."""
-        ms, n = (C.c_double * 3)(), (C.c_uint64 * 3)()
+        {'inter_ms', 'inter_launches' (k_mc), 'res_ms', 'res_launches' (k_res), 'intra_ms', 'intra_launches', 'key_ms', 'key_launches'}."""
+        ms, n = (C.c_double * 4)(), (C.c_uint64 * 4)()
         self._check(self._lib.mobi_batch_get_kernel_times(self._h, ms, n))
-        return {'inter_ms': ms[0], 'inter_launches': n[0], 'intra_ms': ms[1], 'intra_launches': n[1], 'key_ms': ms[2], 'key_launches': n[2]}
+        return {'inter_ms': ms[0], 'inter_launches': n[0], 'intra_ms': ms[1], 'intra_launches': n[1], 'key_ms': ms[2], 'key_launches': n[2],
+                'res_ms': ms[3], 'res_launches': n[3]}
 
     def close(self):
         if getattr(self, '_h', None):

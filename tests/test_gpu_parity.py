@@ -293,9 +293,10 @@ def test_submit_packed_leaf_order_is_free():
     dec.close()
 
 
-def test_per_macroblock_inter_kernel_agrees():
-    """MOBI_INTER_KERNEL=warp selects the one-warp-per-macroblock kernel (kept for comparison); it is read once per
-    process, so the check runs in a child process and compares a digest of every decoded plane with this process's."""
+def test_inter_kernel_variants_agree():
+    """The three formulations of the inter path (mobi_kernels.cu, launch_inter): the default fused kernel, k_mc + k_res
+    (MOBI_INTER_KERNEL=split) and k_inter_v3 (=v3, also with 8-macroblock chunks).  The choice is read once per process,
+    so each variant runs in a child process and the digests of every decoded plane are compared."""
     import hashlib
     import os
     import subprocess
@@ -314,9 +315,9 @@ def test_per_macroblock_inter_kernel_agrees():
         "print(d.hexdigest())\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = {}
-    for kern in ('warp', 'chunk'):
-        env = dict(os.environ, MOBI_INTER_KERNEL=kern, PYTHONPATH=root + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    for kern, envs in (('chunk', {}), ('split', {'MOBI_INTER_KERNEL': 'split'}), ('v3', {'MOBI_INTER_KERNEL': 'v3'}), ('v3_8', {'MOBI_INTER_KERNEL': 'v3', 'MOBI_INTER_CHUNK': '8'})):
+        env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get('PYTHONPATH', ''), **envs)
         r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         out[kern] = r.stdout.strip().splitlines()[-1]
-    assert out['warp'] == out['chunk']
+    assert out['split'] == out['v3'] == out['chunk'] == out['v3_8']

@@ -3,11 +3,11 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi -L; nproc
-for k in ${KERNELS:-chunk}; do
-  echo "=== pytest -m gpu MOBI_INTER_KERNEL=$k"; MOBI_INTER_KERNEL=$k timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+for k in ${KERNELS:-v3}; do
+  echo "=== pytest -m gpu MOBI_INTER_KERNEL=$k"; MOBI_INTER_KERNEL=$k timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -${TAIL:-6}
 done
-for k in ${BENCH_KERNELS:-chunk warp}; do
-  echo "=== bench $k"; MOBI_INTER_KERNEL=$k timeout 400 python bench.py --no-e2e --no-cpu > gpurun_out/bench_$k.json 2> gpurun_out/bench_$k.err
+for k in ${BENCH_KERNELS:-v3 chunk}; do
+  echo "=== bench $k"; MOBI_INTER_KERNEL=$k timeout 400 python bench.py --no-e2e --no-cpu ${BENCH_ARGS:-} > gpurun_out/bench_$k.json 2> gpurun_out/bench_$k.err
   python - <<PY
 import json
 try:
@@ -17,7 +17,7 @@ except Exception as e:
     print('$k', 'bench failed', e); print(open('gpurun_out/bench_$k.err').read()[-1500:])
 PY
 done
-for k in ${NCU_KERNELS:-chunk}; do
+for k in ${NCU_KERNELS:-v3}; do
   echo "=== ncu full $k"
   MOBI_INTER_KERNEL=$k timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_inter' -s 2 -c 1 -f -o gpurun_out/prof_$k python bench.py --profile --steps 2 --warmup 2 > gpurun_out/ncu_full_$k.log 2>&1
   tail -2 gpurun_out/ncu_full_$k.log

@@ -16,7 +16,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, 'mobiclipdecoder_b200', 'lib', 'libmobicuda.so')
-SRC = os.path.join(ROOT, 'mobiclipdecoder_b200', 'csrc', 'mobi_kernels.cu')
+CSRC = os.path.join(ROOT, 'mobiclipdecoder_b200', 'csrc')
 
 
 def line_table(mangled_part):
@@ -31,7 +31,8 @@ def line_table(mangled_part):
             break
         m = re.search(r'//## File "([^"]+)", line (\d+)', l)
         if m:
-            cur = int(m.group(2)) if m.group(1).endswith('mobi_kernels.cu') else -1
+            f = os.path.basename(m.group(1))
+            cur = (f, int(m.group(2))) if os.path.exists(os.path.join(CSRC, f)) else ('', -1)
             continue
         if re.match(r'\s*/\*[0-9a-f]{4}\*/', l):
             lines.append(cur)
@@ -69,18 +70,23 @@ def main():
         for n, c in stall.items():
             tot[n] += float(r[c] or 0)
     T, S = sum(p[0] for p in per.values()), sum(p[1] for p in per.values())
-    src = open(SRC).read().split('\n')
+    src = {}
     print('# %s' % title)
     print('# warp instructions executed: %.0f (%.1f per unit of %.0f), stall samples: %.0f' % (T, T / units, units, S))
     print('# stall reasons: ' + ', '.join('%s %.1f%%' % (n[6:], 100 * v / S) for n, v in tot.most_common(8)))
     print('# shared-memory wavefronts: %.3g, of which excessive (bank conflicts): %.3g' % (sum(p[2] for p in per.values()), sum(p[3] for p in per.values())))
     print('# line  instr/unit  samples%  smem-wavefronts(excess)  source')
-    for ln in sorted(per, key=lambda x: (x is None, x or 0)):
+    for ln in sorted(per, key=lambda x: (x is None, x or ('', 0))):
         n, s, w, e = per[ln]
         if n / units < 0.25 and s / S < 0.003:
             continue
-        text = src[ln - 1].strip()[:110] if ln and ln > 0 else '(inlined CUDA header code: __ldg, __shfl_sync, __funnelshift, __popc ...)'
-        print('%5s %10.1f %8.1f%% %12.0f(%.0f)  %s' % (ln, n / units, 100 * s / S, w, e, text))
+        if ln and ln[1] > 0:
+            if ln[0] not in src:
+                src[ln[0]] = open(os.path.join(CSRC, ln[0])).read().split('\n')
+            text, tag = src[ln[0]][ln[1] - 1].strip()[:110], '%s:%d' % ('v3' if 'v3' in ln[0] else 'k', ln[1])
+        else:
+            text, tag = '(inlined CUDA header code: __ldg, __shfl_sync, __funnelshift, __popc ...)', '-1'
+        print('%8s %10.1f %8.1f%% %12.0f(%.0f)  %s' % (tag, n / units, 100 * s / S, w, e, text))
 
 
 if __name__ == '__main__':
