@@ -191,6 +191,10 @@ int mobi_batch_fetch(mobi_batch_t* b, uint8_t* dst, const uint8_t** view, size_t
 int mobi_batch_stage(mobi_batch_t* b, const uint8_t* const* data, const int* len, int* offset_inout);
 /* Reconstruct staged steps [first, first+count) in order; no host<->device traffic. Asynchronous. */
 int mobi_batch_replay(mobi_batch_t* b, int first, int count);
+/* The same, and every step's new pictures are converted on the device as well (format MOBI_OUT_BGRA: the Bitmap of MD:260-323,
+ * into the batch's device-side output buffer; 0: no conversion): the whole north_star path -- reconstruction and YUV->RGB --
+ * without host<->device traffic. */
+int mobi_batch_replay_convert(mobi_batch_t* b, int first, int count, int format);
 int mobi_batch_staged_steps(const mobi_batch_t* b);
 void mobi_batch_clear_staged(mobi_batch_t* b);
 /* Restore every stream's ring to "no picture decoded" (replay from an I-frame again). */
@@ -215,11 +219,19 @@ int mobi_batch_get_stats(const mobi_batch_t* b, mobi_batch_stats* st);
 int mobi_batch_set_kernel_timing(mobi_batch_t* b, int enabled);
 /* index 0: k_mc (motion compensation of the inter macroblocks); 1: k_intra over the intra macroblocks of P-pictures; 2: k_intra
  * over I-pictures (runs on a second CUDA stream, concurrently with the others); 3: k_res (dequantisation + inverse transforms
- * of the inter macroblocks, added in place) */
-int mobi_batch_get_kernel_times(mobi_batch_t* b, double ms[4], uint64_t launches[4]);
+ * of the inter macroblocks, added in place; only with MOBI_INTER_KERNEL=split); 4: k_bgra (mobi_batch_replay_convert) */
+int mobi_batch_get_kernel_times(mobi_batch_t* b, double ms[5], uint64_t launches[5]);
 void mobi_batch_clear_stats(mobi_batch_t* b);
+/* Where the calling thread's time went since mobi_batch_clear_stats, in milliseconds of wall time: [0] entropy parse (fanned out
+ * over the batch's threads), [1] packing the parsed arrays into the pinned upload arena, [2] enqueueing upload + kernels,
+ * [3] waiting in mobi_batch_fetch for a result's copy-back. */
+int mobi_batch_get_phase_times(const mobi_batch_t* b, double ms[4]);
 
 int mobicuda_abi_version(void);
+/* Device-side exhaustive check of the YUV->RGB kernel's division by (255 - 16) (MD:303-305) against IEEE division: every
+ * normal float32 of magnitude below 2^18 and zero, both signs.  mismatches[0] receives the number of inputs on which they differ
+ * (0 expected), mismatches[1] the bit pattern of the smallest such |x|. */
+int mobicuda_selftest_div239(int device, unsigned long long* mismatches);
 
 #ifdef __cplusplus
 }

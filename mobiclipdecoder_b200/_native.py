@@ -37,6 +37,7 @@ class BatchStats(C.Structure):
 # every symbol include/mobicuda.h declares: name -> (restype, argtypes)
 MOBICUDA_EXPORTS = {
     'mobicuda_abi_version': (C.c_int, []),
+    'mobicuda_selftest_div239': (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong)]),
     'mobi_parser_create': (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]),
     'mobi_parser_destroy': (None, [C.c_void_p]),
     'mobi_parser_parse': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(PackedFrame)]),
@@ -63,6 +64,7 @@ MOBICUDA_EXPORTS = {
     'mobi_batch_last_error': (C.c_char_p, [C.c_void_p]),
     'mobi_batch_stage': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'mobi_batch_replay': (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    'mobi_batch_replay_convert': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     'mobi_batch_staged_steps': (C.c_int, [C.c_void_p]),
     'mobi_batch_clear_staged': (None, [C.c_void_p]),
     'mobi_batch_reset': (C.c_int, [C.c_void_p]),
@@ -71,6 +73,7 @@ MOBICUDA_EXPORTS = {
     'mobi_batch_cuda_stream': (C.c_void_p, [C.c_void_p]),
     'mobi_batch_get_stats': (C.c_int, [C.c_void_p, C.POINTER(BatchStats)]),
     'mobi_batch_clear_stats': (None, [C.c_void_p]),
+    'mobi_batch_get_phase_times': (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     'mobi_batch_set_kernel_timing': (C.c_int, [C.c_void_p, C.c_int]),
     'mobi_batch_get_kernel_times': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }

@@ -1100,42 +1100,103 @@ __global__ void __launch_bounds__(KEY_WARPS * 32, 1) k_intra_key(const DevJob* _
 // ------------------------------------------------------------------------------------------------
 // YUV -> BGRA (MD:260-323): strict binary32, source order, no contraction (file is built with -fmad=false)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bgra(const uint8_t* const* __restrict__ srcs, uint8_t* __restrict__ dst, int pitch, size_t per, Geom g) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= g.W) return;
-    const uint8_t* __restrict__ src = srcs[blockIdx.z];
-    dst += per * blockIdx.z;
-    const int S = g.S;
-    const uint8_t* Y = src;
-    const uint8_t* C = src + (size_t)S * g.H;
-    const float Y2 = (float)Y[y * S + x];
-    const int ci = (y >> 1) * S + (x >> 1), h = S >> 1;
-    float U = (float)C[ci] - 128.0f, V = (float)C[ci + h] - 128.0f;
-    if (x != g.W - 1 && y != g.H - 1) {
-        switch ((x & 1) | ((y & 1) << 1)) {
-        case 1: U += (float)C[ci + 1] - 128.0f; V += (float)C[ci + 1 + h] - 128.0f; U /= 2.0f; V /= 2.0f; break;
-        case 2: U += (float)C[ci + S] - 128.0f; V += (float)C[ci + S + h] - 128.0f; U /= 2.0f; V /= 2.0f; break;
-        case 3:
-            U += (float)C[ci + 1] - 128.0f; V += (float)C[ci + 1 + h] - 128.0f;
-            U += (float)C[ci + S] - 128.0f; V += (float)C[ci + S + h] - 128.0f;
-            U += (float)C[ci + 1 + S] - 128.0f; V += (float)C[ci + 1 + S + h] - 128.0f;
-            U /= 4.0f; V /= 4.0f; break;
-        }
+// x / 239 correctly rounded (== __fdiv_rn(x, 239.0f)) in three instructions: q = RN(x * r) with r = RN(1 / 239), the exact
+// remainder x - 239 q by FMA, one correction step (Markstein's division: exact for a correctly rounded reciprocal).  The
+// general-purpose division is about ten instructions with a slow path, three of them per pixel: it made k_bgra
+// compute-bound (0.36 ms per 1024 pictures against 0.09 ms of memory time).  k_div239_selftest compares the two for EVERY
+// float32 of magnitude below 2^18 on the device itself (mobicuda_selftest_div239; tests/test_gpu_parity.py runs it).
+__device__ __forceinline__ float div239(float x) {
+    const float r = 0x1.12358ep-8f;
+    const float q = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-239.0f, q, x), r, q);
+}
+__global__ void k_div239_selftest(unsigned long long* mismatches) {   // [0] count, [1] smallest |x| (bit pattern) that differs
+    // bit patterns 0x00800000 .. 0x487FFFFF are the normal floats below 2^18 (zero is checked too); both signs
+    const uint32_t lo = 0x00800000u, hi = 0x48800000u;
+    unsigned long long bad = 0, first = ~0ull;
+    for (uint32_t i = lo - 1u + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+        const float x = __uint_as_float(i < lo ? 0u : i);
+        // (bit patterns, except that -0 / 239 comes out as +0: the pixel is clamped at 0 either way)
+        const bool b = i < lo ? (div239(x) != 0.0f || div239(-x) != 0.0f)
+                              : (__float_as_uint(div239(x)) != __float_as_uint(__fdiv_rn(x, 239.0f)) || __float_as_uint(div239(-x)) != __float_as_uint(__fdiv_rn(-x, 239.0f)));
+        if (b) { bad++; if (i < first) first = i; }
     }
+    if (bad) { atomicAdd(mismatches, bad); atomicMin(mismatches + 1, first); }
+}
+
+// One pixel of the bitmap (MD:262-321) from its luma byte and its (averaged) chroma.  Strict binary32 in source order.
+// Clamp to 0..255 and truncation (MD:312-320) are one saturating conversion: cvt.rzi.u8.f32 clamps to the destination's range.
+__device__ __forceinline__ uint32_t sat_u8(float v) {
+    uint32_t r;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t bgra_px(bool moflex, float Y2, float U, float V) {
     float R, G, B;
-    if (g.version == MOBI_MOFLEX3DS) {
+    if (moflex) {
         R = Y2 + 1.420f * V; G = Y2 - 0.344f * U - 0.714f * V; B = Y2 + 1.772f * U;
-        R = __fdiv_rn((R - 16.0f) * 255.0f, 255.0f - 16.0f);
-        G = __fdiv_rn((G - 16.0f) * 255.0f, 255.0f - 16.0f);
-        B = __fdiv_rn((B - 16.0f) * 255.0f, 255.0f - 16.0f);
+        R = div239((R - 16.0f) * 255.0f);   // (c - 16) * 255 / (255 - 16), MD:303-305; |numerator| < 2^17
+        G = div239((G - 16.0f) * 255.0f);
+        B = div239((B - 16.0f) * 255.0f);
     } else {
         R = (float)((int)Y2 + (int)U - (int)V); G = (float)((int)Y2 + (int)V); B = (float)((int)Y2 - (int)U - (int)V);
     }
-    R = R < 0.0f ? 0.0f : (R > 255.0f ? 255.0f : R);
-    G = G < 0.0f ? 0.0f : (G > 255.0f ? 255.0f : G);
-    B = B < 0.0f ? 0.0f : (B > 255.0f ? 255.0f : B);
-    const uint32_t px = (uint32_t)(int)B | (uint32_t)(int)G << 8 | (uint32_t)(int)R << 16 | 0xFF000000u;
-    *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + (size_t)x * 4) = px;
+    return __byte_perm(__byte_perm(sat_u8(B), sat_u8(G), 0x0040), sat_u8(R) | 0xFF00u, 0x5410);
+}
+// (float)n for 0 <= n < 2^23 minus a bias without the conversion pipe (a quarter of the FP32 rate): 2^23 + n is the float whose
+// low mantissa bits are n.  Exact.
+__device__ __forceinline__ float small_int_to_float(uint32_t n, float bias_plus_2p23) { return __uint_as_float(0x4B000000u | n) - bias_plus_2p23; }
+
+// Eight pixels per thread: one 64-bit luma load, the five chroma columns the eight pixels touch as one aligned word + one byte
+// per plane (two rows of them on odd lines), two 16-byte stores.  Width is a multiple of 16, so a picture row is W / 8 threads.
+// The reference averages chroma in float -- (c - 128) summed over the 1, 2 or 4 samples a pixel uses, divided by their number
+// (MD:269-297); these are sums of small integers and divisions by powers of two, so the same VALUE is formed here from an
+// integer sum with one conversion per pixel and plane.
+__global__ void __launch_bounds__(256) k_bgra(const uint8_t* const* __restrict__ srcs, uint8_t* __restrict__ dst, int pitch, size_t per, Geom g, uint32_t wo_magic) {
+    const int wo = g.W >> 3;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)(wo * g.H)) return;
+    const int y = (int)__umulhi(i, wo_magic), x = ((int)i - y * wo) * 8;   // exact: i < 2^26 (magic = ceil(2^32 / wo))
+    const uint8_t* __restrict__ src = srcs[blockIdx.y];
+    const int S = g.S, h = S >> 1;
+    const uint8_t* C = src + (size_t)S * g.H + (y >> 1) * S + (x >> 1);
+    const uint2 yw = *reinterpret_cast<const uint2*>(src + y * S + x);
+    // chroma columns x/2 .. x/2 + 4 of this line's chroma row and (odd lines) the next one.  The fifth column and the next row
+    // are only read where a pixel uses them: not past the picture's last column / row (MD:269).
+    const bool last8 = x + 8 >= g.W, lasty = y == g.H - 1;
+    const bool below = (y & 1) && !lasty;
+    const uint32_t uw = *reinterpret_cast<const uint32_t*>(C), vw = *reinterpret_cast<const uint32_t*>(C + h);
+    uint32_t u[5], v[5];
+#pragma unroll
+    for (int c = 0; c < 4; c++) { u[c] = (uw >> (8 * c)) & 255u; v[c] = (vw >> (8 * c)) & 255u; }
+    u[4] = last8 ? 0u : C[4]; v[4] = last8 ? 0u : C[h + 4];
+    const uint32_t u3top = u[3], v3top = v[3];   // (the last column's odd pixel uses its own sample only, even on an odd line)
+    if (below) {
+        const uint32_t ub = *reinterpret_cast<const uint32_t*>(C + S), vb = *reinterpret_cast<const uint32_t*>(C + S + h);
+#pragma unroll
+        for (int c = 0; c < 4; c++) { u[c] += (ub >> (8 * c)) & 255u; v[c] += (vb >> (8 * c)) & 255u; }
+        if (!last8) { u[4] += C[S + 4]; v[4] += C[S + h + 4]; }
+    }
+    // samples per pixel: even x -> 1 (2 on odd lines), odd x -> twice that, except in the last row / column (none but its own)
+    const float k1 = below ? 0.5f : 1.0f, b1 = below ? 8388608.0f + 256.0f : 8388608.0f + 128.0f;   // even x: scale, 2^23 + 128 * samples
+    const bool horiz = !lasty;                                                                     // odd x may use its right-hand neighbour
+    const float k2 = horiz ? k1 * 0.5f : 1.0f, b2 = horiz ? (below ? 8388608.0f + 512.0f : 8388608.0f + 256.0f) : 8388608.0f + 128.0f;
+    const bool moflex = g.version == MOBI_MOFLEX3DS;
+    uint32_t out[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) {
+        const int c = p >> 1;
+        const float Y2 = small_int_to_float(((p < 4 ? yw.x : yw.y) >> (8 * (p & 3))) & 255u, 8388608.0f);
+        float U, V;
+        if (!(p & 1)) { U = small_int_to_float(u[c], b1) * k1; V = small_int_to_float(v[c], b1) * k1; }
+        else if (p == 7 && (last8 || !horiz)) { U = small_int_to_float(u3top, 8388608.0f + 128.0f); V = small_int_to_float(v3top, 8388608.0f + 128.0f); }
+        else if (horiz) { U = small_int_to_float(u[c] + u[c + 1], b2) * k2; V = small_int_to_float(v[c] + v[c + 1], b2) * k2; }
+        else { U = small_int_to_float(u[c], b2); V = small_int_to_float(v[c], b2); }   // last row (never an odd line's second row: `below` is off)
+        out[p] = bgra_px(moflex, Y2, U, V);
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + per * blockIdx.y + (size_t)y * pitch + (size_t)x * 4);
+    o[0] = make_uint4(out[0], out[1], out[2], out[3]);
+    o[1] = make_uint4(out[4], out[5], out[6], out[7]);
 }
 
 // strided planes -> tight I420, 4 bytes per thread
@@ -1285,9 +1346,23 @@ cudaError_t launch_gate(const uint32_t* resident, uint32_t target, cudaStream_t 
 
 cudaError_t launch_bgra(const uint8_t* const* srcs, int n, uint8_t* dst, int dst_pitch, size_t dst_picture_bytes, Geom g, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    dim3 grid((unsigned)((g.W + 255) / 256), (unsigned)g.H, (unsigned)n);
-    k_bgra<<<grid, 256, 0, st>>>(srcs, dst, dst_pitch, dst_picture_bytes, g);
+    const int wo = g.W >> 3, items = wo * g.H;   // eight pixels per thread
+    const uint32_t magic = (uint32_t)((0x100000000ull + (uint64_t)wo - 1) / (uint64_t)wo);
+    dim3 grid((unsigned)((items + 255) / 256), (unsigned)n);
+    k_bgra<<<grid, 256, 0, st>>>(srcs, dst, dst_pitch, dst_picture_bytes, g, magic);
     return cudaGetLastError();
+}
+
+cudaError_t selftest_div239(unsigned long long* mismatches_host) {
+    unsigned long long* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 2 * sizeof *d);
+    if (e != cudaSuccess) return e;
+    const unsigned long long init[2] = {0ull, ~0ull};
+    cudaMemcpy(d, init, sizeof init, cudaMemcpyHostToDevice);
+    k_div239_selftest<<<148 * 16, 256>>>(d);
+    e = cudaMemcpy(mismatches_host, d, 2 * sizeof *d, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e;
 }
 
 cudaError_t launch_pack_i420(const uint8_t* const* srcs, int n, uint8_t* dst, Geom g, cudaStream_t st) {

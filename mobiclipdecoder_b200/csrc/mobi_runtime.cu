@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -110,7 +111,7 @@ struct Arena {
 // Where one step's arrays live on the device, plus the host-side facts needed to launch it again.
 struct StepLayout {
     size_t bytes = 0;
-    size_t jobs_off = 0, work_off = 0, key_off = 0;   // job table, intra work list, {job, work_base} of the I-pictures
+    size_t jobs_off = 0, work_off = 0, key_off = 0, pics_off = 0;   // job table, intra work list, {job, work_base} of the I-pictures, luma plane of each job's new picture
     int n_jobs = 0, n_inter_jobs = 0, n_key_jobs = 0;
     uint32_t n_work = 0;      // all intra macroblocks; the list holds those of P-pictures first, then those of I-pictures
     uint32_t n_work_p = 0;    // intra macroblocks inside P-pictures
@@ -280,9 +281,12 @@ public:
             if (out_h_) cudaFreeHost(out_h_);
             if (ptr_d_) cudaFree(ptr_d_);
             if (ptr_h_) cudaFreeHost(ptr_h_);
-            for (int w = 0; w < 4; w++) for (cudaEvent_t e : ev_[w]) cudaEventDestroy(e);
+            for (int w = 0; w < 5; w++) for (cudaEvent_t e : ev_[w]) cudaEventDestroy(e);
             if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
             if (copy_) { cudaStreamSynchronize(copy_); cudaStreamDestroy(copy_); }
+            if (conv_) { cudaStreamSynchronize(conv_); cudaStreamDestroy(conv_); }
+            if (conv_go_) cudaEventDestroy(conv_go_);
+            if (conv_done_) cudaEventDestroy(conv_done_);
             if (fork_) cudaEventDestroy(fork_);
             if (join_) cudaEventDestroy(join_);
             for (cudaEvent_t e : ev_free_) cudaEventDestroy(e);
@@ -373,7 +377,10 @@ public:
         if (!data || !len || !offset) return set_err(MOBI_ERR_ARG, "null argument");
         if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
         rc_.assign(N_, MOBI_OK);
+        const auto t0 = std::chrono::steady_clock::now();
         pool_.run(N_, [&](int i) { rc_[i] = parse_one(i, data[i], len[i], &offset[i], count_[i]); });
+        const auto t1 = std::chrono::steady_clock::now();
+        phase_ms_[0] += std::chrono::duration<double, std::milli>(t1 - t0).count();
         views_.resize(N_);
         int n_ok = 0, first_bad = -1;
         for (int i = 0; i < N_; i++) {
@@ -387,6 +394,8 @@ public:
         cur_arena_ ^= 1;
         StepLayout L;
         int rc = pack_step(a, L, count_);
+        const auto t2 = std::chrono::steady_clock::now();
+        phase_ms_[1] += std::chrono::duration<double, std::milli>(t2 - t1).count();
         if (rc != MOBI_OK) return rc;
         if (!ok(cudaMemcpyAsync(a.d, a.h, L.bytes, cudaMemcpyHostToDevice, stream_), "H2D arena")) return MOBI_ERR_CUDA;
         stats_.h2d_bytes += L.bytes;
@@ -395,6 +404,7 @@ public:
         cudaEventRecord(a.consumed, stream_);
         a.pending = true;
         for (int s : L.job_stream) count_[s]++;
+        phase_ms_[2] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t2).count();
         return (first_bad >= 0 && N_ == 1) ? rc_[first_bad] : MOBI_OK;
     }
 
@@ -448,13 +458,44 @@ public:
         staged_.push_back(std::move(st));
         return MOBI_OK;
     }
-    int replay(int first, int count) {
+    // format 0: reconstruction only; MOBI_OUT_BGRA: every step's new pictures are also converted (k_bgra) into the device-side
+    // output buffer.  Nothing crosses PCIe either way.
+    int replay(int first, int count, int format = 0) {
         if (first < 0 || count < 0 || first + count > (int)staged_.size()) return set_err(MOBI_ERR_ARG, "replay range outside staged steps");
+        if (format != 0 && format != 2) return set_err(MOBI_ERR_ARG, "replay converts to BGRA (2) or not at all (0)");
         if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
+        const size_t per = (size_t)W_ * H_ * 4;
+        if (format) {
+            int rc = ensure_out(per * N_);
+            if (rc != MOBI_OK) return rc;
+            if (!conv_ && !ok(cudaStreamCreateWithFlags(&conv_, cudaStreamNonBlocking), "cudaStreamCreate")) return MOBI_ERR_CUDA;
+            if (!conv_go_ && (!ok(cudaEventCreateWithFlags(&conv_go_, cudaEventDisableTiming), "cudaEventCreate") ||
+                              !ok(cudaEventCreateWithFlags(&conv_done_, cudaEventDisableTiming), "cudaEventCreate"))) return MOBI_ERR_CUDA;
+        }
         for (int k = first; k < first + count; k++) {
             int rc = launch_step(staged_[k].d, staged_[k].L);
             if (rc != MOBI_OK) return rc;
             for (int s : staged_[k].L.job_stream) count_[s]++;
+            if (format) {
+                const StepLayout& L = staged_[k].L;
+                // MOBI_BGRA_STREAM=own puts the conversion on a stream of its own, beside the next step's reconstruction.  Measured
+                // (B200, 1024 x 400x240): the two then fight for the same SMs and memory system -- k_bgra 0.38 ms instead of 0.12,
+                // the inter kernel 0.60 instead of 0.26, 0.70 ms per step instead of 0.48 -- so the default is back to back.
+                static const bool own = [] { const char* e = getenv("MOBI_BGRA_STREAM"); return e && !strcmp(e, "own"); }();
+                cudaStream_t cs = own ? conv_ : stream_;
+                if (own) {
+                    if (!ok(cudaEventRecord(conv_go_, stream_), "cudaEventRecord")) return MOBI_ERR_CUDA;
+                    if (!ok(cudaStreamWaitEvent(conv_, conv_go_, 0), "cudaStreamWaitEvent")) return MOBI_ERR_CUDA;
+                }
+                if (timing_) tick(4, cs);
+                if (!ok(launch_bgra(reinterpret_cast<const uint8_t* const*>(staged_[k].d + L.pics_off), L.n_jobs, out_d_, (int)W_ * 4, per, g_, cs), "k_bgra")) return MOBI_ERR_CUDA;
+                if (timing_) tick(4, cs);
+                stats_.launches++;
+            }
+        }
+        if (format && count > 0) {   // whoever waits for the batch's stream waits for the last conversion too
+            if (!ok(cudaEventRecord(conv_done_, conv_), "cudaEventRecord")) return MOBI_ERR_CUDA;
+            if (!ok(cudaStreamWaitEvent(stream_, conv_done_, 0), "cudaStreamWaitEvent")) return MOBI_ERR_CUDA;
         }
         return MOBI_OK;
     }
@@ -617,7 +658,9 @@ public:
         if (slots_used_ == 0) return set_err(MOBI_ERR_STATE, "no result outstanding");
         if (!ok(cudaSetDevice(dev_), "cudaSetDevice")) return MOBI_ERR_CUDA;
         OutSlot& o = slot_[(slot_head_ + 2 - slots_used_) & 1];
+        const auto t0 = std::chrono::steady_clock::now();
         if (!ok(cudaEventSynchronize(o.ready), "cudaEventSynchronize")) return MOBI_ERR_CUDA;
+        phase_ms_[3] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         slots_used_--;
         if (dst) {
             const size_t per = o.bytes / N_;
@@ -641,11 +684,12 @@ public:
         ev_[which].push_back(e);
     }
     // which: 0 the inter kernel (k_mc; the fused kernel where one is selected), 1 k_intra over P-pictures, 2 k_intra over
-    // I-pictures (side stream), 3 k_res
+    // I-pictures (side stream), 3 k_res, 4 k_bgra (replay with conversion; its own stream)
     int kernel_times(double* ms_out, uint64_t* n_out) {
         int rc = sync();
         if (rc != MOBI_OK) return rc;
-        for (int w = 0; w < 4; w++) {
+        if (conv_ && !ok(cudaStreamSynchronize(conv_), "cudaStreamSynchronize")) return MOBI_ERR_CUDA;
+        for (int w = 0; w < 5; w++) {
             double ms = 0; uint64_t n = 0;
             for (size_t i = 0; i + 1 < ev_[w].size(); i += 2) {
                 float t = 0;
@@ -668,7 +712,10 @@ public:
     const char* error() const { return err_.c_str(); }
     void* cuda_stream() const { return (void*)stream_; }
     const mobi_batch_stats& stats() const { return stats_; }
-    void clear_stats() { std::memset(&stats_, 0, sizeof stats_); }
+    void clear_stats() { std::memset(&stats_, 0, sizeof stats_); std::memset(phase_ms_, 0, sizeof phase_ms_); }
+    // host wall time since clear_stats: entropy parse (all threads, wall), packing into the pinned arena, enqueueing the
+    // upload and the kernels, waiting in fetch for a result's copy-back
+    void phase_times(double* ms) const { for (int i = 0; i < 4; i++) ms[i] = phase_ms_[i]; }
     int n_streams() const { return N_; }
     uint32_t width() const { return W_; }
     uint32_t height() const { return H_; }
@@ -743,6 +790,7 @@ private:
         }
         L.work_off = p; p = align_up(p + sizeof(IntraWork) * L.n_work, 256);
         L.key_off = p; p = align_up(p + 8 * (size_t)L.n_jobs, 256);
+        L.pics_off = p; p = align_up(p + sizeof(void*) * (size_t)L.n_jobs, 256);
         for (int j = 0; j < L.n_jobs; j++) {
             const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr;
             Off& o = off[j];
@@ -762,6 +810,7 @@ private:
         int rc = ensure_arena(a, L.bytes);
         if (rc != MOBI_OK) return rc;
         DevJob* jobs = reinterpret_cast<DevJob*>(a.h + L.jobs_off);
+        const uint8_t** pics = reinterpret_cast<const uint8_t**>(a.h + L.pics_off);
         pool_.run(L.n_jobs, [&](int j) {
             const int s = L.job_stream[j];
             const mobi_packed_frame& f = views_[s];
@@ -783,6 +832,7 @@ private:
             J.intra = reinterpret_cast<const uint32_t*>(a.d + o.intra);
             const int c = count[s];
             J.dst = picture(s, c);
+            pics[j] = J.dst;
             for (int k = 1; k <= 5; k++) J.ref[k - 1] = k <= c ? picture(s, c - k) : nullptr;
             J.dst_pic = (uint32_t)(s * RING + c % RING);
             for (int k = 1; k <= 5; k++) J.ref_pic[k - 1] = k <= c ? (uint32_t)(s * RING + (c - k) % RING) : 0u;
@@ -939,7 +989,8 @@ private:
     uint32_t* ticket_ = nullptr;
     uint32_t ticket_base_ = 0, inter_ticket_base_[2] = {0, 0}, stamp_ = 0, key_resident_ = 0;   // ticket_[0]: work tickets of k_intra; ticket_[16], [32]: chunk tickets of k_mc, k_res; ticket_[48]: resident I-picture CTAs
     InterMaps tm_;
-    cudaStream_t side_ = nullptr, copy_ = nullptr;
+    cudaStream_t side_ = nullptr, copy_ = nullptr, conv_ = nullptr;
+    cudaEvent_t conv_go_ = nullptr, conv_done_ = nullptr;
     cudaEvent_t fork_ = nullptr, join_ = nullptr;
     std::vector<std::vector<uint16_t>> depth_;
     std::vector<uint32_t> bucket_;
@@ -952,10 +1003,11 @@ private:
     const uint8_t** ptr_d_ = nullptr;
     const uint8_t** ptr_h_ = nullptr;
     bool timing_ = false;
-    std::vector<cudaEvent_t> ev_[4], ev_free_;
+    std::vector<cudaEvent_t> ev_[5], ev_free_;
     OutSlot slot_[2];
     int slot_head_ = 0, slots_used_ = 0;
     mobi_batch_stats stats_{};
+    double phase_ms_[4] = {0, 0, 0, 0};
     uint32_t quant_override_ = 0, yuv_override_ = 0;
     bool have_override_ = false;
     std::string err_;
@@ -993,6 +1045,12 @@ int mobi_packed_validate(uint32_t width, uint32_t height, int version, const mob
         if (rc != MOBI_OK && err && err_len) { strncpy(err, v.err_.c_str(), err_len - 1); err[err_len - 1] = 0; }
         return rc;
     } catch (...) { return MOBI_ERR_NOMEM; }
+}
+
+int mobicuda_selftest_div239(int device, unsigned long long* mismatches) {
+    if (!mismatches) return MOBI_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return MOBI_ERR_CUDA;
+    return mobi::selftest_div239(mismatches) == cudaSuccess ? MOBI_OK : MOBI_ERR_CUDA;
 }
 
 int mobi_create(uint32_t width, uint32_t height, int version, int device, mobi_t** out) {
@@ -1061,7 +1119,8 @@ int mobi_batch_stage(mobi_batch_t* b, const uint8_t* const* data, const int* len
     if (!b) return MOBI_ERR_ARG;
     try { return b->b.stage(data, len, offset_inout); } catch (...) { return b->b.set_err(MOBI_ERR_NOMEM, "out of host memory"); }
 }
-int mobi_batch_replay(mobi_batch_t* b, int first, int count) { return b ? b->b.replay(first, count) : MOBI_ERR_ARG; }
+int mobi_batch_replay(mobi_batch_t* b, int first, int count) { return b ? b->b.replay(first, count, 0) : MOBI_ERR_ARG; }
+int mobi_batch_replay_convert(mobi_batch_t* b, int first, int count, int format) { return b ? b->b.replay(first, count, format) : MOBI_ERR_ARG; }
 int mobi_batch_staged_steps(const mobi_batch_t* b) { return b ? b->b.staged_steps() : 0; }
 void mobi_batch_clear_staged(mobi_batch_t* b) { if (b) b->b.clear_staged(); }
 int mobi_batch_reset(mobi_batch_t* b) { return b ? b->b.reset(false) : MOBI_ERR_ARG; }
@@ -1074,12 +1133,17 @@ int mobi_batch_get_stats(const mobi_batch_t* b, mobi_batch_stats* st) {
     return MOBI_OK;
 }
 void mobi_batch_clear_stats(mobi_batch_t* b) { if (b) b->b.clear_stats(); }
+int mobi_batch_get_phase_times(const mobi_batch_t* b, double ms[4]) {
+    if (!b || !ms) return MOBI_ERR_ARG;
+    b->b.phase_times(ms);
+    return MOBI_OK;
+}
 int mobi_batch_set_kernel_timing(mobi_batch_t* b, int enabled) {
     if (!b) return MOBI_ERR_ARG;
     b->b.set_timing(enabled != 0);
     return MOBI_OK;
 }
-int mobi_batch_get_kernel_times(mobi_batch_t* b, double ms[4], uint64_t launches[4]) {
+int mobi_batch_get_kernel_times(mobi_batch_t* b, double ms[5], uint64_t launches[5]) {
     return b ? b->b.kernel_times(ms, launches) : MOBI_ERR_ARG;
 }
 

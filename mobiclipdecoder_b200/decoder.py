@@ -285,8 +285,10 @@ class MobiBatch:
         self._check(self._lib.mobi_batch_stage(self._h, self._ptrs, self._lens, self._offs))
         return list(self._offs)
 
-    def replay(self, first, count):
-        self._check(self._lib.mobi_batch_replay(self._h, first, count))
+    def replay(self, first, count, fmt=0):
+        """Reconstruct staged steps [first, first + count); fmt = MobiBatch.OUT_BGRA also converts every step's new pictures
+        on the device (no copies)."""
+        self._check(self._lib.mobi_batch_replay_convert(self._h, first, count, fmt) if fmt else self._lib.mobi_batch_replay(self._h, first, count))
 
     def staged_steps(self):
         return self._lib.mobi_batch_staged_steps(self._h)
@@ -341,16 +343,22 @@ class MobiBatch:
     def clear_stats(self):
         self._lib.mobi_batch_clear_stats(self._h)
 
+    def phase_times(self):
+        """Host wall time since clear_stats(), ms: {'parse', 'pack', 'enqueue', 'fetch_wait'} (mobi_batch_get_phase_times)."""
+        ms = (C.c_double * 4)()
+        self._check(self._lib.mobi_batch_get_phase_times(self._h, ms))
+        return {'parse': ms[0], 'pack': ms[1], 'enqueue': ms[2], 'fetch_wait': ms[3]}
+
     def set_kernel_timing(self, on):
         self._check(self._lib.mobi_batch_set_kernel_timing(self._h, 1 if on else 0))
 
     def kernel_times(self):
         """Per-kernel device time since the last call (synchronises):
         {'inter_ms', 'inter_launches' (k_mc), 'res_ms', 'res_launches' (k_res), 'intra_ms', 'intra_launches', 'key_ms', 'key_launches'}."""
-        ms, n = (C.c_double * 4)(), (C.c_uint64 * 4)()
+        ms, n = (C.c_double * 5)(), (C.c_uint64 * 5)()
         self._check(self._lib.mobi_batch_get_kernel_times(self._h, ms, n))
         return {'inter_ms': ms[0], 'inter_launches': n[0], 'intra_ms': ms[1], 'intra_launches': n[1], 'key_ms': ms[2], 'key_launches': n[2],
-                'res_ms': ms[3], 'res_launches': n[3]}
+                'res_ms': ms[3], 'res_launches': n[3], 'bgra_ms': ms[4], 'bgra_launches': n[4]}
 
     def close(self):
         if getattr(self, '_h', None):

@@ -321,3 +321,13 @@ def test_inter_kernel_variants_agree():
         assert r.returncode == 0, r.stderr[-2000:]
         out[kern] = r.stdout.strip().splitlines()[-1]
     assert out['split'] == out['v3'] == out['chunk'] == out['v3_8']
+
+
+def test_bgra_division_is_ieee_division_for_every_input():
+    """k_bgra divides by (255 - 16) with a three-instruction sequence instead of the general IEEE division; the library
+    compares the two on the device for every float32 of magnitude below 2^18 (the numerator is below 2^17)."""
+    import ctypes as C
+    from mobiclipdecoder_b200 import _native
+    bad = (C.c_ulonglong * 2)(12345, 0)
+    assert _native.mobicuda().mobicuda_selftest_div239(0, bad) == 0
+    assert bad[0] == 0, '%d inputs differ, the smallest has bit pattern 0x%08x' % (bad[0], bad[1])
