@@ -218,6 +218,7 @@ def main():
     ap.add_argument('--repeats', type=int, default=0, help='replays of the K staged steps inside the timed region of the value leg (0 = enough for 0.3 s)')
     ap.add_argument('--cpu-seconds', type=float, default=1.5, help='wall budget of the cpu_baseline sample (x host threads = CPU work)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-affinity', action='store_true', help='N > 1: do not pin each rank to its own slice of the host cores')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the config 2 / config 3 / un-staggered legs')
     ap.add_argument('--profile', action='store_true', help='short run for ncu: value leg only')
@@ -233,7 +234,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     K, Wm = args.steps, max(args.warmup, 3 if args.impl == 'native' and not args.profile else args.warmup)
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     threads = args.threads if args.threads > 0 else max(1, cores // max(1, world))
 
     from mobiclipdecoder_b200.workloads import CONFIGS
@@ -273,6 +274,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        if not args.no_affinity:
+            # each rank parses on its own slice of the host cores (and first-touches its pinned arenas from there)
+            my_cores = sharding.pin_to_cores(local_rank, world)
+            threads = args.threads if args.threads > 0 else max(1, len(my_cores))
     dev = torch.device('cuda', local_rank)
     D = dist if world > 1 else None
 
@@ -425,6 +430,7 @@ def main():
             s1 = batch.stats()
             ph = batch.phase_times()
             ms_ = sharding.max_over_ranks(D, max(ev_ms, wall_ms), torch, dev)
+            per_rank = sharding.gather_objects(D, dict({k_: round(v / K, 3) for k_, v in ph.items()}, wall=round(wall_ms / K, 3), threads=threads))
             return {'value': world * S * K / (ms_ * 1e-3), 'unit': UNIT,
                     'h2d_bytes_per_step': (s1['h2d_bytes'] - s0['h2d_bytes']) / K, 'd2h_bytes_per_step': (s1['d2h_bytes'] - s0['d2h_bytes']) / K,
                     'ms_per_step': ms_ / K, 'output': label, 'host_threads': threads,
@@ -432,6 +438,7 @@ def main():
                     # where rank 0's calling thread spent the step (host wall time per step): the parse fans out over host_threads;
                     # fetch_wait is the time the host had nothing left to do but wait for the copy-back
                     'host_ms_per_step': {k_: v / K for k_, v in ph.items()},
+                    'host_ms_per_step_by_rank': per_rank if world > 1 else None,
                     'd2h_gbps_per_gpu': (s1['d2h_bytes'] - s0['d2h_bytes']) / K / (ms_ / K * 1e-3) / 1e9}
 
         e2e = run_e2e(BGRA, 'BGRA bitmaps (W*H*4 per frame) in pinned host memory')

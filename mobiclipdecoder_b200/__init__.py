@@ -6,5 +6,5 @@ side above it: :class:`MobiclipDecoder` mirrors the reference's
 :class:`MobiBatch` exposes the lock-step multi-stream path.  There is no CPU fallback: if the CUDA library is
 missing or no GPU is present, construction raises.
 """
-from .decoder import MobiclipDecoder, MobiclipVersion, MobiBatch, MobiParser, MobiError  # noqa: F401
+from .decoder import MobiclipDecoder, MobiclipVersion, MobiBatch, MobiMultiBatch, MobiParser, MobiError  # noqa: F401
 from .synth import SynthParams, SynthStream  # noqa: F401

@@ -307,6 +307,8 @@ public:
         cudaDeviceProp prop;
         if (!ok(cudaGetDeviceProperties(&prop, dev_), "cudaGetDeviceProperties")) return MOBI_ERR_CUDA;
         sm_count_ = prop.multiProcessorCount;
+        key_ticket_threshold_ = sm_count_;
+        if (const char* e = getenv("MOBI_KEY_TICKETS")) key_ticket_threshold_ = atoi(e);   // experiments: 0 = always by ticket, a huge value = never
         if (!ok(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate")) return MOBI_ERR_CUDA;
         if (!ok(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking), "cudaStreamCreate")) return MOBI_ERR_CUDA;
         if (!ok(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking), "cudaStreamCreate")) return MOBI_ERR_CUDA;
@@ -877,11 +879,18 @@ private:
             }
             // P-pictures' intra macroblocks: counting sort by depth.  I-pictures: raster order per picture (the row kernel
             // indexes work[work_base + m]), pictures one after the other behind the P list.
+            // One CTA per I-picture suits the few I-pictures of a staggered step (they hide behind the inter kernel on a few
+            // SMs).  A step with more I-pictures than SMs would run them in waves of one picture-latency each (measured: 1024
+            // pictures, 7 waves, 2.0 ms); such a step is throughput-bound, not latency-bound, and its macroblocks go through
+            // the depth-ordered ticket list with everything else (all pictures' wavefronts advance together).
+            int n_ipics = 0;
+            for (int j = 0; j < L.n_jobs; j++) { const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr; if (h.n_intra == h.n_mb) n_ipics++; }
+            const bool ipics_by_ticket = n_ipics > key_ticket_threshold_;
             bucket_.assign((size_t)maxd + 2, 0);
             uint32_t* cnt = bucket_.data();
             for (int j = 0; j < L.n_jobs; j++) {
                 const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr;
-                if (h.n_intra == h.n_mb) { L.n_key_jobs++; continue; }
+                if (h.n_intra == h.n_mb && !ipics_by_ticket) { L.n_key_jobs++; continue; }
                 L.n_work_p += h.n_intra;
                 const uint16_t* per_rank = depth_[j].data() + h.n_mb;
                 for (uint32_t r = 0; r < h.n_intra; r++) cnt[per_rank[2 * r]]++;
@@ -893,7 +902,7 @@ private:
             for (int j = 0; j < L.n_jobs; j++) {
                 const mobi_packed_frame& f = views_[L.job_stream[j]];
                 const mobi_frame_hdr& h = *f.hdr;
-                const bool key = h.n_intra == h.n_mb;
+                const bool key = h.n_intra == h.n_mb && !ipics_by_ticket;
                 const uint16_t* per_rank = depth_[j].data() + h.n_mb;
                 if (key) { keytab[2 * n_key] = (uint32_t)j; keytab[2 * n_key + 1] = key_at; n_key++; }
                 for (uint32_t r = 0; r < h.n_intra; r++) {
@@ -977,6 +986,7 @@ private:
     uint32_t n_mb_;
     size_t ysz_, pic_;
     int sm_count_ = 148;
+    int key_ticket_threshold_ = 148;   // more I-pictures than this in one step: ticket list instead of one CTA per picture (MOBI_KEY_TICKETS overrides)
     Pool pool_;
     std::vector<std::unique_ptr<Parser>> parsers_;
     std::vector<ParsedFrame> frames_;

@@ -370,3 +370,86 @@ class MobiBatch:
             self.close()
         except Exception:
             pass
+
+
+class MobiMultiBatch:
+    """All GPUs of one node from ONE process -- the shape the reference's host has (one C# process, one decoder object per
+    stream, MobiclipDecoder.cs:13-61): a MobiBatch per device, each driven from its own host thread (ctypes drops the GIL
+    for the duration of a native call, and the library selects its device on every call), global stream g living on
+    device g % n_devices (sharding.streams_of_rank).  Nothing crosses devices: streams are independent."""
+
+    def __init__(self, Width, Height, Version, n_streams, devices, n_threads=0):
+        from concurrent.futures import ThreadPoolExecutor
+        from . import sharding
+        self.devices = list(devices)
+        if not self.devices or n_streams < len(self.devices):
+            raise ValueError('need at least one stream per device')
+        world = len(self.devices)
+        self.n_streams = int(n_streams)
+        self.owned = [sharding.streams_of_rank(self.n_streams, r, world) for r in range(world)]
+        per_dev_threads = n_threads if n_threads > 0 else max(1, len(sharding.cores_of_rank(0, world)))
+        self.parts = [MobiBatch(Width, Height, Version, len(self.owned[r]), device=d, n_threads=per_dev_threads) for r, d in enumerate(self.devices)]
+        self.Width, self.Height = self.parts[0].Width, self.parts[0].Height
+        self._pool = [ThreadPoolExecutor(max_workers=1) for _ in self.devices]   # one thread per device, calls stay in order
+
+    def _each(self, fn):
+        futs = [self._pool[r].submit(fn, r, b) for r, b in enumerate(self.parts)]
+        return [f.result() for f in futs]
+
+    def _split(self, per_stream):
+        return [[per_stream[g] for g in own] for own in self.owned]
+
+    def _merge(self, per_part):
+        out = [None] * self.n_streams
+        for own, vals in zip(self.owned, per_part):
+            for g, v in zip(own, vals):
+                out[g] = v
+        return out
+
+    def decode(self, frames, offsets=None):
+        """One frame per global stream.  Returns (offsets after, status), both in global stream order."""
+        fr, of = self._split(frames), (self._split(offsets) if offsets is not None else [None] * len(self.parts))
+        res = self._each(lambda r, b: b.decode(fr[r], of[r]))
+        return self._merge([o for o, _ in res]), self._merge([s for _, s in res])
+
+    def submit(self, frames, fmt=MobiBatch.OUT_I420):
+        fr = self._split(frames)
+        self._each(lambda r, b: b.submit(fr[r], fmt=fmt) and None)
+
+    def fetch(self):
+        """Oldest outstanding result of every device, as uint8 [n_streams, bytes per stream] in global stream order."""
+        res = self._each(lambda r, b: b.fetch())
+        out = np.empty((self.n_streams, res[0].shape[1]), dtype=np.uint8)
+        for own, a in zip(self.owned, res):
+            out[own] = a
+        return out
+
+    def read_yuv(self):
+        res = self._each(lambda r, b: b.read_yuv())
+        out = np.empty((self.n_streams, res[0].shape[1]), dtype=np.uint8)
+        for own, a in zip(self.owned, res):
+            out[own] = a
+        return out
+
+    def read_bgra_all(self):
+        res = self._each(lambda r, b: b.read_bgra_all())
+        out = np.empty((self.n_streams, self.Height, self.Width, 4), dtype=np.uint8)
+        for own, a in zip(self.owned, res):
+            out[own] = a
+        return out
+
+    def sync(self):
+        self._each(lambda r, b: b.sync())
+
+    def close(self):
+        for b in self.parts:
+            b.close()
+        for p in self._pool:
+            p.shutdown(wait=True)
+        self.parts = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -44,3 +44,33 @@ def sum_over_ranks(dist, value, torch, device='cpu'):
 
 def aggregate_fps(frames_per_rank_total, max_ms):
     return frames_per_rank_total / (max_ms * 1e-3)
+
+
+def cores_of_rank(local_rank, local_world, available=None):
+    """The host cores rank `local_rank` of `local_world` parses on: an equal, contiguous slice of the cores this process may
+    run on.  Contiguous, because Linux numbers the cores of one socket consecutively and GPUs k and k+1 hang off the same
+    socket on the 8-GPU boards: the parse threads, the pinned arenas they fill (first touch) and the GPU's PCIe root then
+    sit on one NUMA node."""
+    cores = sorted(available if available is not None else os.sched_getaffinity(0))
+    per = max(1, len(cores) // max(1, local_world))
+    lo = (local_rank * per) % len(cores)
+    return cores[lo:lo + per] or cores
+
+
+def pin_to_cores(local_rank, local_world):
+    """Restrict this process (and every thread it starts from now on) to its slice.  Returns the slice."""
+    mine = cores_of_rank(local_rank, local_world)
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        pass
+    return mine
+
+
+def gather_objects(dist, obj):
+    """Every rank's `obj`, in rank order (a list of one when not distributed)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return [obj]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out

@@ -331,3 +331,27 @@ def test_bgra_division_is_ieee_division_for_every_input():
     bad = (C.c_ulonglong * 2)(12345, 0)
     assert _native.mobicuda().mobicuda_selftest_div239(0, bad) == 0
     assert bad[0] == 0, '%d inputs differ, the smallest has bit pattern 0x%08x' % (bad[0], bad[1])
+
+
+@pytest.mark.parametrize('name,w,h', [('mods_256x192', 256, 192), ('moflex_400x240', 400, 240)])
+def test_step_of_many_i_pictures_goes_by_ticket_and_is_bit_exact(name, w, h):
+    """More I-pictures in one step than the GPU has SMs: their macroblocks join the depth-ordered ticket list of k_intra
+    instead of one k_intra_key CTA per picture (mobi_runtime.cu pack_step).  160 streams, all on their I-picture in step 0
+    (and again at the GOP boundary, together), P-pictures in between through the usual path."""
+    _, _, ver, _ = CONFIGS[name]
+    n_streams, n_frames = 160, 4
+    gens = [make_stream(name, 7000 + s) for s in range(n_streams)]
+    oracles = [Oracle(w, h, ver) for _ in range(n_streams)]
+    b = MobiBatch(w, h, ver, n_streams, n_threads=4)
+    for f in range(n_frames):
+        batch_in = [g.next_frame()[0] for g in gens]
+        offs, status = b.decode(batch_in)
+        assert all(st == 0 for st in status)
+        for s in range(n_streams):
+            ok, off, _ = oracles[s].decode(batch_in[s], 0, False)
+            assert ok and off == offs[s]
+        if f in (0, n_frames - 1):
+            got = b.read_yuv()
+            for s in range(n_streams):
+                assert np.array_equal(got[s], oracles[s].i420()), 'stream %d frame %d' % (s, f)
+    b.close()

@@ -47,7 +47,8 @@ def _worker(rank, world, port, out):
     local_ms = 10.0 + 5.0 * rank
     worst = sharding.max_over_ranks(dist, local_ms, torch)
     total = sharding.sum_over_ranks(dist, frames, torch)
-    out[rank] = (mine, worst, total)
+    everyone = sharding.gather_objects(dist, {'rank': rank, 'streams': mine})
+    out[rank] = (mine, worst, total, everyone)
     dist.destroy_process_group()
 
 
@@ -60,4 +61,15 @@ def test_two_ranks_gloo():
     for r in range(world):
         assert out[r][1] == 15.0      # the slowest rank's time, on every rank
         assert out[r][2] == 18.0      # all frames of all ranks
+        assert [e['rank'] for e in out[r][3]] == [0, 1] and out[r][3][1]['streams'] == [1, 3, 5]
     assert sharding.aggregate_fps(18, 15.0) == pytest.approx(1200.0)
+
+
+def test_core_slices_are_disjoint_and_cover():
+    cores = list(range(32))
+    for world in (1, 2, 4, 8):
+        slices = [sharding.cores_of_rank(r, world, cores) for r in range(world)]
+        assert sorted(c for s in slices for c in s) == cores
+        assert all(s == list(range(s[0], s[0] + len(s))) for s in slices)       # contiguous: one socket per rank
+    assert sharding.cores_of_rank(5, 8, [0, 1, 2]) != []                          # fewer cores than ranks: shared, never empty
+    assert sharding.gather_objects(None, 7) == [7]
