@@ -748,10 +748,30 @@ __device__ __forceinline__ int plane_val(const uint8_t* t, int ts, int delta, in
     return N == 8 ? (A + run + 64) >> 7 : (A + run + 16) >> 5;
 }
 
-// One intra op: predict an NxN block inside a shared tile (t = its top-left pixel, 4-byte aligned).  Predictors read
-// only pixels outside the block, so values are computed and stored without an intermediate barrier.
+// Predicted pixels + their parked residuals, clipped (the "+ residual, clip" half of loc_116518 / loc_116628 MD:2898-2956).
+__device__ __forceinline__ uint32_t add_res4(uint32_t px, const int16_t* rp) {
+    const uint2 rr = *reinterpret_cast<const uint2*>(rp);
+    const int p0 = (int)(px & 255u) + (int)(int16_t)(rr.x & 0xFFFFu), p1 = (int)((px >> 8) & 255u) + ((int)rr.x >> 16);
+    const int p2 = (int)((px >> 16) & 255u) + (int)(int16_t)(rr.y & 0xFFFFu), p3 = (int)(px >> 24) + ((int)rr.y >> 16);
+    uint32_t hi, out;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(p3), "r"(p2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(p1), "r"(p0), "r"(hi));
+    return out;
+}
+__device__ __forceinline__ uint32_t add_res2(uint32_t px, const int16_t* rp) {
+    const uint32_t rr = *reinterpret_cast<const uint32_t*>(rp);
+    const int p0 = (int)(px & 255u) + (int)(int16_t)(rr & 0xFFFFu), p1 = (int)((px >> 8) & 255u) + ((int)rr >> 16);
+    uint32_t out;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(p1), "r"(p0), "r"(0));
+    return out;
+}
+
+// One intra op: predict an NxN block inside a shared tile (t = its top-left pixel, 4-byte aligned) and, when the block is
+// coded, add its residual (rp, row pitch rs) in the same pass: the lane that computed a pixel's prediction also holds its
+// residual, so a block costs one store and one warp barrier (this is the wavefront's critical path).  Predictors read only
+// pixels outside the block, so values are computed and stored without an intermediate barrier.
 template <int N>
-__device__ __forceinline__ void intra_predict(uint8_t* t, int ts, int mode, int delta, bool left_av, bool top_av, int lane) {
+__device__ __forceinline__ void intra_predict(uint8_t* t, int ts, int mode, int delta, bool left_av, bool top_av, bool res, const int16_t* rp, int rs, int lane) {
     constexpr int WORDS = N * N / 4, WPR = N / 4;  // 4-pixel words in the block / per row
     if (mode == 3) {  // DC by flat-offset availability (MD:1920-2022, 2501-2580)
         unsigned sum = 0;
@@ -768,7 +788,10 @@ __device__ __forceinline__ void intra_predict(uint8_t* t, int ts, int mode, int 
         else if (top_av || left_av) dc = (sum + N / 2) / N;
         else dc = 0x80;
         const uint32_t w = (dc & 255u) * 0x01010101u;
-        for (int i = lane; i < WORDS; i += 32) *reinterpret_cast<uint32_t*>(t + (i / WPR) * ts + (i % WPR) * 4) = w;
+        for (int i = lane; i < WORDS; i += 32) {
+            const int y = i / WPR, x = (i % WPR) * 4;
+            *reinterpret_cast<uint32_t*>(t + y * ts + x) = res ? add_res4(w, rp + y * rs + x) : w;
+        }
     } else if (mode == 2) {
         // the reference ORs four unclipped values into one u32 (MD:3064-3074, 3212-3219, 3314-3321): a value outside
         // 0..255 bleeds into the bytes above it, and the top byte's overflow is lost
@@ -776,23 +799,21 @@ __device__ __forceinline__ void intra_predict(uint8_t* t, int ts, int mode, int 
             const int y = i / WPR, x = (i % WPR) * 4;
             const uint32_t w = (uint32_t)plane_val<N>(t, ts, delta, x, y) | (uint32_t)plane_val<N>(t, ts, delta, x + 1, y) << 8 |
                                (uint32_t)plane_val<N>(t, ts, delta, x + 2, y) << 16 | (uint32_t)plane_val<N>(t, ts, delta, x + 3, y) << 24;
-            *reinterpret_cast<uint32_t*>(t + y * ts + x) = w;
+            *reinterpret_cast<uint32_t*>(t + y * ts + x) = (N != 16 && res) ? add_res4(w, rp + y * rs + x) : w;
         }
     } else if (N == 8) {
         // directional predictors: every value is a byte (averages of bytes), so the pixels spread over all 32 lanes --
-        // two neighbours per lane, one 16-bit store -- instead of four per lane on half the warp: this sits on the
-        // wavefront's critical path
+        // two neighbours per lane, one 16-bit store -- instead of four per lane on half the warp
         const int y = lane >> 2, x = (lane & 3) * 2;
-        const uint32_t w = (uint32_t)dir_px<N>(t, ts, mode, x, y) | (uint32_t)dir_px<N>(t, ts, mode, x + 1, y) << 8;
+        uint32_t w = (uint32_t)dir_px<N>(t, ts, mode, x, y) | (uint32_t)dir_px<N>(t, ts, mode, x + 1, y) << 8;
+        if (res) w = add_res2(w, rp + y * rs + x);
         *reinterpret_cast<uint16_t*>(t + y * ts + x) = (uint16_t)w;
     } else if (N == 4) {
-        if (lane < 16) { const int y = lane >> 2, x = lane & 3; t[y * ts + x] = (uint8_t)dir_px<N>(t, ts, mode, x, y); }
-    } else {
-        for (int i = lane; i < WORDS; i += 32) {
-            const int y = i / WPR, x = (i % WPR) * 4;
-            const uint32_t w = (uint32_t)dir_px<N>(t, ts, mode, x, y) | (uint32_t)dir_px<N>(t, ts, mode, x + 1, y) << 8 |
-                               (uint32_t)dir_px<N>(t, ts, mode, x + 2, y) << 16 | (uint32_t)dir_px<N>(t, ts, mode, x + 3, y) << 24;
-            *reinterpret_cast<uint32_t*>(t + y * ts + x) = w;
+        if (lane < 16) {
+            const int y = lane >> 2, x = lane & 3;
+            int v = dir_px<N>(t, ts, mode, x, y);
+            if (res) v = clip255(v + (int)rp[y * rs + x]);
+            t[y * ts + x] = (uint8_t)v;
         }
     }
     __syncwarp();
@@ -863,21 +884,14 @@ __device__ __forceinline__ void intra_residuals(IntraSmem& sm, const uint32_t* _
     }
     __syncwarp();
 }
-// Parked residuals of an NxN block added onto the tile (the "+ residual, clip" half of loc_116518 / loc_116628 MD:2898-2956).
+// A coded block without a predictor (modes 9 / 19): the residual lands on whatever the tile holds.
 template <int N>
 __device__ __forceinline__ void add_resid(uint8_t* t, int ts, const int16_t* rp, int rpitch, int lane) {
     constexpr int WORDS = N * N / 4, WPR = N / 4;
     if (lane < WORDS) {
         const int y = lane / WPR, x = (lane % WPR) * 4;
         uint32_t* pw = reinterpret_cast<uint32_t*>(t + y * ts + x);
-        const uint2 rr = *reinterpret_cast<const uint2*>(rp + y * rpitch + x);
-        const uint32_t px = *pw;
-        const int p0 = (int)(px & 255u) + (int)(int16_t)(rr.x & 0xFFFFu), p1 = (int)((px >> 8) & 255u) + ((int)rr.x >> 16);
-        const int p2 = (int)((px >> 16) & 255u) + (int)(int16_t)(rr.y & 0xFFFFu), p3 = (int)(px >> 24) + ((int)rr.y >> 16);
-        uint32_t hi, out;
-        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(p3), "r"(p2), "r"(0));
-        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(p1), "r"(p0), "r"(hi));
-        *pw = out;
+        *pw = add_res4(*pw, rp + y * rpitch + x);
     }
     __syncwarp();
 }
@@ -908,11 +922,10 @@ __device__ __forceinline__ uint32_t intra_prefetch(const DevJob& J, IntraSmem& s
     for (int i = lane; i < 52; i += 32) z[i] = make_uint4(0, 0, 0, 0);
     return myop;
 }
-// Stage the neighbourhood, run the ops in stream order on the tiles, write the macroblock out.
-__device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g, IntraSmem& sm, const IntraItem& it, uint32_t myop, int lane, const int PLANES) {
+// Stage the neighbourhood from the picture in global memory (the general form: any macroblock of any picture).
+__device__ __forceinline__ void intra_stage_global(const DevJob& J, const Geom& g, IntraSmem& sm, const IntraItem& it, int lane, const int PLANES) {
     const int S = g.S;
     const uint32_t m = it.m;
-    const int n_ops = (int)((it.info >> 2) & 127u), n_coef = (int)((it.info >> 9) & 511u);
     const int mbx = (int)(m % (uint32_t)g.mbw), mby = (int)(m / (uint32_t)g.mbw);
     const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
     // One round of independent aligned word loads.  luma: 7 words of row y-1 (columns x-4..x+23), then columns
@@ -935,24 +948,29 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
             dstw = reinterpret_cast<uint32_t*>(&sm.u.t.y[1 + r][20 + 4 * h]); flat = yoff + r * S + 16 + 4 * h; chroma = false;
         }
     };
-    {
-        const int n = 45 + (wrap ? 32 : 0);
-        uint32_t* d0; uint32_t* d1; int f0, f1; bool c0, c1;
-        slot(lane, d0, f0, c0);
-        const bool two = lane + 32 < n;
-        slot(two ? lane + 32 : lane, d1, f1, c1);
-        const bool w0 = PLANES == 3 || c0 == (PLANES == 2), w1 = two && (PLANES == 3 || c1 == (PLANES == 2));   // this plane group's slots only
-        const uint32_t v0 = !w0 ? 0u : c0 ? nb_chroma4(J, g, f0, m) : nb_luma4(J, g, f0, m);
-        const uint32_t v1 = !w1 ? 0u : c1 ? nb_chroma4(J, g, f1, m) : nb_luma4(J, g, f1, m);
-        if (w0) *d0 = v0;
-        if (w1) *d1 = v1;
-        if ((PLANES & 1) && lane + 64 < n) {   // only in the wrap case (luma)
-            slot(lane + 64, d0, f0, c0);
-            *d0 = nb_luma4(J, g, f0, m);
-        }
+    const int n = 45 + (wrap ? 32 : 0);
+    uint32_t* d0; uint32_t* d1; int f0, f1; bool c0, c1;
+    slot(lane, d0, f0, c0);
+    const bool two = lane + 32 < n;
+    slot(two ? lane + 32 : lane, d1, f1, c1);
+    const bool w0 = PLANES == 3 || c0 == (PLANES == 2), w1 = two && (PLANES == 3 || c1 == (PLANES == 2));   // this plane group's slots only
+    const uint32_t v0 = !w0 ? 0u : c0 ? nb_chroma4(J, g, f0, m) : nb_luma4(J, g, f0, m);
+    const uint32_t v1 = !w1 ? 0u : c1 ? nb_chroma4(J, g, f1, m) : nb_luma4(J, g, f1, m);
+    if (w0) *d0 = v0;
+    if (w1) *d1 = v1;
+    if ((PLANES & 1) && lane + 64 < n) {   // only in the wrap case (luma)
+        slot(lane + 64, d0, f0, c0);
+        *d0 = nb_luma4(J, g, f0, m);
     }
     __syncwarp();
-
+}
+// Run the macroblock's ops in stream order on the staged tiles (fixed block order, each block sees the previous block's
+// reconstruction: MD:1759-1880, 2776-2902).
+__device__ __forceinline__ void intra_ops(const Geom& g, IntraSmem& sm, const IntraItem& it, uint32_t myop, int lane, const int PLANES) {
+    const int S = g.S;
+    const int n_ops = (int)((it.info >> 2) & 127u);
+    const int mbx = (int)(it.m % (uint32_t)g.mbw), mby = (int)(it.m / (uint32_t)g.mbw);
+    const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
     for (int k = 0; k < n_ops; k++) {
         const uint32_t op = __shfl_sync(0xffffffffu, myop, k);
         const int mode = (int)(op & 31u), plane = (int)((op >> 6) & 3u), x4 = (int)((op >> 8) & 3u), y4 = (int)((op >> 10) & 3u);
@@ -967,16 +985,21 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
         }
         const bool left_av = ((off - (plane == 2 ? (S >> 1) : 0)) & (S - 1)) != 0;  // MD:1923, VOffsetfix MD:1885
         const bool top_av = off >= S;                                               // MD:1924
-        if (mode == 20) intra_predict<16>(tp, ts, 2, delta, left_av, top_av, lane);
+        if (mode == 20) intra_predict<16>(tp, ts, 2, delta, left_av, top_av, false, rp, rs, lane);
         else if (mode >= 10) {
-            if (mode != 19) intra_predict<4>(tp, ts, mode - 10, delta, left_av, top_av, lane);
-            if (res) add_resid<4>(tp, ts, rp, rs, lane);
+            if (mode != 19) intra_predict<4>(tp, ts, mode - 10, delta, left_av, top_av, res, rp, rs, lane);
+            else if (res) add_resid<4>(tp, ts, rp, rs, lane);
         } else {
-            if (mode != 9) intra_predict<8>(tp, ts, mode, delta, left_av, top_av, lane);
-            if (res) add_resid<8>(tp, ts, rp, rs, lane);
+            if (mode != 9) intra_predict<8>(tp, ts, mode, delta, left_av, top_av, res, rp, rs, lane);
+            else if (res) add_resid<8>(tp, ts, rp, rs, lane);
         }
     }
-    // write the macroblock out
+}
+// Write the macroblock out.
+__device__ __forceinline__ void intra_store(const DevJob& J, const Geom& g, IntraSmem& sm, const IntraItem& it, int lane, const int PLANES) {
+    const int S = g.S;
+    const int mbx = (int)(it.m % (uint32_t)g.mbw), mby = (int)(it.m / (uint32_t)g.mbw);
+    const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
     if (PLANES & 1) {
         const int lrow = lane >> 1, lhalf = lane & 1;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.u.t.y[1 + lrow][4 + lhalf * 8]);
@@ -987,6 +1010,11 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
         const uint32_t cv = *reinterpret_cast<const uint32_t*>(&sm.u.t.c[cpl][1 + crow][4 + chalf * 4]);
         *reinterpret_cast<uint32_t*>(J.dst + (size_t)S * g.H + coff + (cpl ? (S >> 1) : 0) + crow * S + chalf * 4) = cv;
     }
+}
+__device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g, IntraSmem& sm, const IntraItem& it, uint32_t myop, int lane, const int PLANES) {
+    intra_stage_global(J, g, sm, it, lane, PLANES);
+    intra_ops(g, sm, it, myop, lane, PLANES);
+    intra_store(J, g, sm, it, lane, PLANES);
 }
 
 // Scattered intra macroblocks (those inside P-pictures): persistent warps draw tickets from a dependency-depth-ordered
@@ -1027,20 +1055,39 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 8) k_intra(const DevJob* __r
 
 // I-pictures: one CTA per picture, TWO warps per macroblock row -- one walks the row's luma, the other its chroma (no
 // predictor reads across planes, so they are independent wavefronts and the per-macroblock chain of dependent steps
-// shrinks to the longer of the two) -- macroblocks of a row left to right, rows r, r + KEY_ROWS, ... per warp pair.  The
-// left neighbour is the warp's own previous macroblock; the rows above are awaited through per-row, per-plane-group
-// progress counters in shared memory, so the wavefront's per-level latency is the macroblock's own work plus one L2 round
-// trip for the neighbour pixels -- no flag traffic through L2.  All rows of a picture live in one CTA, so every awaited
-// row is resident: no deadlock.
+// shrinks to the longer of the two) -- macroblocks of a row left to right, rows r, r + KEY_ROWS, ... per warp pair.
+// Every neighbour pixel a macroblock's predictors can read was produced inside this CTA, so none of them is fetched from
+// the picture: the left column is the warp's own previous macroblock (kept in a register per lane), the row above comes
+// from a line buffer in shared memory that each row's warp fills with the bottom pixel line of its macroblocks, and the
+// few places where flat addressing (SURVEY.md 8a hazard 2) reaches further when Width == Stride -- pixel line 14 of the
+// row above's last macroblock (top-left of column 0), the first eight columns of this row's first macroblock (right of the
+// last column) -- are kept beside it.  A macroblock is published (per-row progress counter in shared memory) as soon as
+// its line is in the buffer; its global stores follow, off the wavefront's critical path, and nobody reads them back.
+// All rows of a picture live in one CTA, so every awaited row is resident: no deadlock.
 constexpr int KEY_ROWS = 16, KEY_WARPS = 2 * KEY_ROWS;
 struct KeyPic { uint32_t job, work_base; };
+struct KeyShared {   // behind the KEY_WARPS per-warp IntraSmem blocks
+    uint32_t prog[2][64];          // macroblocks finished per macroblock row (H <= 1024), luma / chroma; accessed with atomics only
+    uint32_t tail[2][KEY_ROWS];    // luma: pixel line 14, last four columns of the row's last macroblock; chroma: V line 6, likewise
+    uint8_t first8[KEY_ROWS][16][8];   // luma columns 0..7 of the row's first macroblock
+    // then: uint8_t line_y[KEY_ROWS][S], line_c[KEY_ROWS][S] (chroma lines as in the picture: U | V)
+};
+__host__ __device__ inline size_t key_smem_bytes(int S) { return KEY_WARPS * sizeof(IntraSmem) + sizeof(KeyShared) + 2 * (size_t)KEY_ROWS * (size_t)S; }
 
 // PLANES is a run-time value here on purpose: one copy of the (large) intra code serves both wavefronts, and the
 // instruction cache is what a handful of latency-bound warps live on.
-__device__ __forceinline__ void key_rows(const DevJob& J, const IntraWork* __restrict__ items, const Geom& g, IntraSmem& sm, uint32_t* prog, int first_row, int lane, const int PLANES) {
-    const int mbw = g.mbw;
+__device__ __forceinline__ void key_rows(const DevJob& J, const IntraWork* __restrict__ items, const Geom& g, IntraSmem& sm, KeyShared& ks, uint8_t* lines,
+                                         int first_row, int lane, const int PLANES) {
+    const int mbw = g.mbw, S = g.S, W = g.W;
+    const bool full = W == S;                      // flat addressing wraps onto real pixels
+    uint32_t* prog = ks.prog[PLANES - 1];
+    uint8_t* line_all = lines + (PLANES == 2 ? KEY_ROWS * S : 0);
     for (int row = first_row; row < g.mbh; row += KEY_ROWS) {
+        const int slot = row % KEY_ROWS, pslot = (row + KEY_ROWS - 1) % KEY_ROWS;
+        uint8_t* my_line = line_all + slot * S;
+        const uint8_t* up_line = line_all + pslot * S;
         IntraItem it_next = load_item(items + row * mbw);
+        uint32_t leftw = 0;   // luma: lane k < 16 holds columns 12..15 of line k of the previous macroblock; chroma: lanes 0-7 U, 8-15 V, columns 4..7
         for (int x = 0; x < mbw; x++) {
             // the next macroblock's work item travels one iteration ahead, and its ops and coefficient records are pulled
             // into L1 while this one is reconstructed: two dependent trips to memory less on the wavefront's critical path
@@ -1058,7 +1105,7 @@ __device__ __forceinline__ void key_rows(const DevJob& J, const IntraWork* __res
                 if ((it.wait & 8u) && x + 1 < mbw) need1 = max(need1, (uint32_t)x + 2u);
                 while (atomicAdd(&prog[row - 1], 0u) < need1) __nanosleep(20);
                 if (need2 && row > 1) while (atomicAdd(&prog[row - 2], 0u) < need2) __nanosleep(20);
-                __threadfence_block();   // the producer fenced at gpu scope before moving its counter; the pixel loads below bypass L1
+                __threadfence_block();
             }
             __syncwarp();
             if (x + 1 < mbw) {
@@ -1067,24 +1114,86 @@ __device__ __forceinline__ void key_rows(const DevJob& J, const IntraWork* __res
                 if ((uint32_t)lane * 128u < bytes) asm volatile("prefetch.global.L1 [%0];" :: "l"(c1 + lane * 128));
                 if (lane == 31) asm volatile("prefetch.global.L1 [%0];" :: "l"(J.ops + it_next.first_op));
             }
-            intra_reconstruct(J, g, sm, it, myop, lane, PLANES);
+            // ---- stage the neighbourhood from shared memory (what nb_luma4 / nb_chroma4 would return, resolved in place) ----
+            if (PLANES == 1) {
+                if (lane < 16) {          // left column, lines 0..15: columns x-4..x-1
+                    uint32_t v = leftw;
+                    if (x == 0) v = (full && lane == 0 && row > 0) ? *reinterpret_cast<const uint32_t*>(up_line + S - 4) : 0u;   // flat address - 4 = the line above, last columns
+                    *reinterpret_cast<uint32_t*>(&sm.u.t.y[1 + lane][0]) = v;
+                } else if (lane < 23) {   // the line above: columns x-4 .. x+23
+                    const int col = x * 16 - 4 + 4 * (lane - 16);
+                    uint32_t v = 0;
+                    if (col >= S) { if (mbw > 1) v = *reinterpret_cast<const uint32_t*>(&ks.first8[slot][0][col - S]); }   // (full) wraps onto line 0 of this row's first macroblock
+                    else if (row > 0) {
+                        if (col < 0) { if (full) v = ks.tail[0][pslot]; }      // pixel line y-2, columns S-4..: line 14 of the row above's last macroblock
+                        else if (col < W) v = *reinterpret_cast<const uint32_t*>(up_line + col);
+                    }
+                    *reinterpret_cast<uint32_t*>(&sm.u.t.y[0][4 * (lane - 16)]) = v;
+                }
+                if (full && x == mbw - 1 && mbw > 1) {   // right of the last column: lines 1..15 of this row's first macroblock, one line down
+                    const int r = lane >> 1, h = lane & 1;
+                    if (r < 15) *reinterpret_cast<uint32_t*>(&sm.u.t.y[1 + r][20 + 4 * h]) = *reinterpret_cast<const uint32_t*>(&ks.first8[slot][r + 1][4 * h]);
+                }
+            } else {
+                if (lane < 16) {          // left columns of U (lanes 0-7) and V (8-15)
+                    const int pl = lane >> 3, k = lane & 7;
+                    uint32_t v = leftw;
+                    if (x == 0) v = (full && pl == 0 && k == 0 && row > 0) ? *reinterpret_cast<const uint32_t*>(up_line + S - 4) : 0u;   // U's left at column 0: V's last columns, one line up
+                    *reinterpret_cast<uint32_t*>(&sm.u.t.c[pl][1 + k][0]) = v;
+                } else if (lane < 22) {   // the line above: three words per plane
+                    const int pl = (lane - 16) / 3, q = (lane - 16) % 3;
+                    const int fc = pl * (S >> 1) + x * 8 - 4 + 4 * q;          // column inside the S-wide chroma line (U | V)
+                    uint32_t v = 0;
+                    if (row > 0) {
+                        if (fc < 0) { if (full) v = ks.tail[1][pslot]; }       // chroma line c-2, V's last columns
+                        else if (fc < S) {
+                            const int pc = fc < (S >> 1) ? fc : fc - (S >> 1);
+                            if (pc < (W >> 1)) v = *reinterpret_cast<const uint32_t*>(up_line + fc);
+                        }
+                    }
+                    *reinterpret_cast<uint32_t*>(&sm.u.t.c[pl][0][4 * q]) = v;
+                }
+            }
+            __syncwarp();
+            intra_ops(g, sm, it, myop, lane, PLANES);
+            // ---- hand the macroblock's edges on: next macroblock (register), row below (line buffer) ----
+            if (row >= KEY_ROWS && lane == 0) {
+                // the slot still holds the line of row - KEY_ROWS, which row - KEY_ROWS + 1 reads up to a macroblock ahead
+                const uint32_t need = (uint32_t)min(mbw, x + 2);
+                while (atomicAdd(&prog[row - KEY_ROWS + 1], 0u) < need) __nanosleep(20);
+            }
+            __syncwarp();
+            if (PLANES == 1) {
+                if (lane < 16) leftw = *reinterpret_cast<const uint32_t*>(&sm.u.t.y[1 + lane][16]);
+                else if (lane < 20) *reinterpret_cast<uint32_t*>(my_line + x * 16 + 4 * (lane - 16)) = *reinterpret_cast<const uint32_t*>(&sm.u.t.y[16][4 + 4 * (lane - 16)]);
+                else if (lane == 20 && x == mbw - 1) ks.tail[0][slot] = *reinterpret_cast<const uint32_t*>(&sm.u.t.y[15][16]);
+                if (x == 0) { const int r = lane >> 1, h = lane & 1; *reinterpret_cast<uint32_t*>(&ks.first8[slot][r][4 * h]) = *reinterpret_cast<const uint32_t*>(&sm.u.t.y[1 + r][4 + 4 * h]); }
+            } else {
+                if (lane < 16) leftw = *reinterpret_cast<const uint32_t*>(&sm.u.t.c[lane >> 3][1 + (lane & 7)][8]);
+                else if (lane < 20) {
+                    const int pl = (lane - 16) >> 1, j = (lane - 16) & 1;
+                    *reinterpret_cast<uint32_t*>(my_line + pl * (S >> 1) + x * 8 + 4 * j) = *reinterpret_cast<const uint32_t*>(&sm.u.t.c[pl][8][4 + 4 * j]);
+                } else if (lane == 20 && x == mbw - 1) ks.tail[1][slot] = *reinterpret_cast<const uint32_t*>(&sm.u.t.c[1][7][8]);
+            }
             __syncwarp();
             if (lane == 0) {
-                __threadfence();            // the row's pixels are in L2 before the counter moves
+                __threadfence_block();      // the line is in shared memory before the counter moves
                 atomicExch(&prog[row], (uint32_t)x + 1u);
             }
+            intra_store(J, g, sm, it, lane, PLANES);
         }
     }
 }
 
 __global__ void __launch_bounds__(KEY_WARPS * 32, 1) k_intra_key(const DevJob* __restrict__ jobs, const IntraWork* __restrict__ work,
                                                                  const KeyPic* __restrict__ pics, Geom g, uint32_t* resident) {
-    extern __shared__ __align__(16) uint8_t s_key_raw[];   // KEY_WARPS x IntraSmem: above the 48 KB static limit
+    extern __shared__ __align__(16) uint8_t s_key_raw[];   // KEY_WARPS x IntraSmem, KeyShared, the line buffers: above the 48 KB static limit
     IntraSmem* s_all = reinterpret_cast<IntraSmem*>(s_key_raw);
-    __shared__ uint32_t s_prog[2][64];   // macroblocks finished per macroblock row (H <= 1024), luma / chroma; accessed with atomics only
+    KeyShared& ks = *reinterpret_cast<KeyShared*>(s_key_raw + KEY_WARPS * sizeof(IntraSmem));
+    uint8_t* lines = s_key_raw + KEY_WARPS * sizeof(IntraSmem) + sizeof(KeyShared);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) atomicAdd(resident, 1u);   // this CTA holds its SM resources now (see k_gate)
-    if (threadIdx.x < 128) s_prog[threadIdx.x >> 6][threadIdx.x & 63] = 0;
+    if (threadIdx.x < 128) ks.prog[threadIdx.x >> 6][threadIdx.x & 63] = 0;
     __syncthreads();
     IntraSmem& sm = s_all[warp];
     const KeyPic pic = pics[blockIdx.x];
@@ -1094,7 +1203,7 @@ __global__ void __launch_bounds__(KEY_WARPS * 32, 1) k_intra_key(const DevJob* _
         const uint32_t* qt = J.hdr->qtab;
         for (int i = lane; i < 80; i += 32) sm.qtab[i] = __ldg(qt + i);
     }
-    key_rows(J, items, g, sm, s_prog[warp & 1], warp >> 1, lane, 1 + (warp & 1));
+    key_rows(J, items, g, sm, ks, lines, warp >> 1, lane, 1 + (warp & 1));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1323,9 +1432,9 @@ cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_w
 cudaError_t launch_intra_key(const DevJob* jobs, const IntraWork* work, const void* pics, int n_pics, Geom g, uint32_t* resident, cudaStream_t st) {
     if (n_pics <= 0) return cudaSuccess;
     // per device, so set on every launch (a host-side table lookup)
-    const cudaError_t attr = cudaFuncSetAttribute(k_intra_key, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KEY_WARPS * sizeof(IntraSmem)));
+    const cudaError_t attr = cudaFuncSetAttribute(k_intra_key, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)key_smem_bytes(g.S));
     if (attr != cudaSuccess) return attr;
-    k_intra_key<<<(unsigned)n_pics, KEY_WARPS * 32, KEY_WARPS * sizeof(IntraSmem), st>>>(jobs, work, reinterpret_cast<const KeyPic*>(pics), g, resident);
+    k_intra_key<<<(unsigned)n_pics, KEY_WARPS * 32, key_smem_bytes(g.S), st>>>(jobs, work, reinterpret_cast<const KeyPic*>(pics), g, resident);
     return cudaGetLastError();
 }
 
