@@ -122,3 +122,44 @@ class Moc5Reader:
             if rc < 0:
                 raise MobiError(rc, 'MOC5 block header outside the file')
             yield off.value, bs.value
+
+
+class MoflexPlayer:
+    """What the reference player does with the frames MoLiveDemux hands it (MobiclipDecoder/Form1.cs:508-545,
+    d_OnCompleteFrameReceived): the first video stream seen becomes THE video stream; one decoder object decodes every one of
+    its frames; a MoLiveStreamVideoWithLayout chunk whose ImageLayout is not Simple2D (6) marks the stream as stereoscopic --
+    the two eyes' pictures alternate in the stream (and in the decoder's ring, so every frame must be decoded), the first,
+    third, ... are shown and the frame period doubles (Form1.cs:516-528).  Audio chunks are not handled here.
+
+    make_decoder(width, height) returns an object with Data / Offset / DecodeFrame() (mobiclipdecoder_b200.MobiclipDecoder,
+    or a stand-in).  on_frame() returns None for chunks the player ignores, else a dict: bitmap (what DecodeFrame returned),
+    present (shown or only decoded), period_ms (time until the next presented frame), eye ('left' / 'right' / None)."""
+    SIMPLE_2D = 6   # MoLiveStreamVideoWithLayout.VideoLayout.Simple2D (MoLiveStreamVideoWithLayout.cs:10-19)
+
+    def __init__(self, make_decoder):
+        self._make = make_decoder
+        self.decoder = None
+        self.PlayingVideoStream = -1
+        self.Is3D = False
+        self.left = False
+
+    def on_frame(self, chunk, data):
+        if chunk.chunk_id not in (1, 3) or not (self.PlayingVideoStream == -1 or chunk.stream_index == self.PlayingVideoStream):
+            return None
+        self.left = not self.left
+        if self.decoder is None:
+            self.decoder = self._make(chunk.width, chunk.height)
+            self.PlayingVideoStream = chunk.stream_index
+            self.Is3D = chunk.chunk_id == 3 and chunk.image_layout != self.SIMPLE_2D
+        self.decoder.Data, self.decoder.Offset = data, 0
+        bitmap = self.decoder.DecodeFrame()
+        present = (not self.Is3D) or self.left
+        period = (2000.0 if self.Is3D else 1000.0) / (chunk.fps_rate / chunk.fps_scale)
+        return {'bitmap': bitmap, 'present': present, 'period_ms': period, 'eye': None if not self.Is3D else ('left' if self.left else 'right')}
+
+    def play(self, demux):
+        """Drive a MoLiveDemux to its end (the CLI's stop conditions); yields on_frame()'s results for the video stream."""
+        for chunk, data in demux.frames():
+            r = self.on_frame(chunk, data)
+            if r is not None:
+                yield r

@@ -26,7 +26,7 @@ REF = os.environ.get('MOBI_REFERENCE_DIR', '/root/reference')
 OUT = os.path.join(HERE, '_ref')
 
 PRIMS = r'(?:byte|sbyte|ushort|short|uint|int|ulong|long|float|bool)'
-STATIC_CLASSES = r'(?:IOUtil|MobiConst|MobiConstRef|Array|Color|ImageLockMode|PixelFormat|MobiclipVersion|FrameUtil|Math)'
+STATIC_CLASSES = r'(?:IOUtil|MobiConst|MobiConstRef|Array|Color|ImageLockMode|PixelFormat|MobiclipVersion|FrameUtil|Math|MoLive)'
 
 
 def cs_to_cpp(src: str) -> str:
@@ -60,6 +60,92 @@ def cs_to_cpp(src: str) -> str:
     last = src.rstrip().rfind('}')
     cls = src.rfind('}', 0, last)
     src = src[:cls] + '};' + src[cls + 1:]
+    return src
+
+
+
+# ---- containers: classes with reference semantics, inheritance, Stream / Dictionary / delegates -------------------------
+REF_CLASSES = ['MoLiveChunk', 'MoLiveStream', 'MoLiveStreamCodec', 'MoLiveStreamVideo', 'MoLiveStreamVideoWithLayout', 'MoLiveStreamAudio',
+               'MoLiveStreamTimeline', 'MoLiveChunkFoo', 'MoLiveInBitStream', 'Endpoint', 'ModsHeader', 'KeyFrameInfo']
+# identifiers that hold a reference to a class instance in these files: `x.` becomes `x->`
+PTR_VARS = ['chunk', 'Chunk', 'p', 'bs', 'Reader', 'Stream', 'Header', 'mDestinationStream', 'Destination', 'dst', 'src']
+
+
+def close_structs(src: str) -> str:
+    """C++ wants `};` after every struct body (nested ones too)."""
+    out, i = [], 0
+    for m in re.finditer(r'\bstruct\s+\w+[^;{()]*\{', src):
+        depth, j = 0, m.end() - 1
+        while True:
+            if src[j] == '{':
+                depth += 1
+            elif src[j] == '}':
+                depth -= 1
+                if depth == 0:
+                    break
+            j += 1
+        out.append(j)
+    for j in sorted(out, reverse=True):
+        if not src[j + 1:].lstrip().startswith(';'):
+            src = src[:j + 1] + ';' + src[j + 1:]
+    return src
+
+
+def cs_container_to_cpp(src: str) -> str:
+    """The same kind of rewriting as cs_to_cpp -- spellings only, no statement of container logic is touched -- for the
+    container classes: a C# class instance is a reference, so variables of those types become pointers (and `.` on them
+    `->`), `out` parameters references, properties fields, virtual / override / abstract their C++ spellings, object
+    initialisers a statement expression, System.IO.Stream the CsStream of ref_shim.h."""
+    src = src.lstrip('﻿')
+    for a, b in (('UInt64', 'ulong'), ('UInt32', 'uint'), ('UInt16', 'ushort'), ('Byte', 'byte')):
+        src = re.sub(r'\b%s\b' % a, b, src)
+    src = re.sub(r'public\s+(\w+(?:\[\])*)\s+(\w+)\s*\{\s*get;\s*(?:private\s+)?set;\s*\}', r'public \1 \2;', src)
+    src = re.sub(r'public\s+delegate\s+void\s+(\w+)\s*\(([^)]*)\)\s*;', r'typedef std::function<void(\2)> \1;', src)
+    src = re.sub(r'public\s+event\s+(\w+)\s+(\w+)\s*;', r'\1 \2;', src)
+    src = re.sub(r'public\s+enum\s+(\w+)(\s*:\s*\w+)?\s*\{([^}]*)\}', r'enum \1\2 {\3};', src)
+    # class headers; `base` is the one base class named there
+    m = re.search(r'class\s+\w+\s*:\s*(\w+)', src)
+    if m:
+        src = re.sub(r'\bbase\.', m.group(1) + '::', src)
+        src = re.sub(r':\s*base\s*\(', ': ' + m.group(1) + '(', src)
+    src = re.sub(r'(?:public|private)\s+(?:abstract\s+)?class\s+(\w+)', r'struct \1', src)
+    src = re.sub(r'\babstract\s+([\w\[\]<>]+)\s+(\w+)\s*\(([^)]*)\)\s*;', r'virtual \1 \2(\3) = 0;', src)
+    src = re.sub(r'\b(?:sealed\s+)?override\s+([\w\[\]<>]+)\s+(\w+)\s*\(([^)]*)\)', r'virtual \1 \2(\3) override', src)
+    # forward declarations of nested classes at the top of the enclosing one (members may name them before their definition)
+    top = re.search(r'struct\s+(\w+)[^{;]*\{', src)
+    if top:
+        nested = [n for n in re.findall(r'struct\s+(\w+)[^{;]*\{', src[top.end():])]
+        if nested:
+            src = src[:top.end()] + ' ' + ' '.join('struct %s;' % n for n in nested) + src[top.end():]
+    # object initialisers: new X() { A = 1, B = 2 }
+    def obj_init(mm):
+        sets = ' '.join('o_->%s;' % part.strip() for part in mm.group(2).split(',') if part.strip())
+        return '({ %s* o_ = new %s(); %s o_; })' % (mm.group(1), mm.group(1), sets)
+    src = re.sub(r'new\s+(\w+)\s*\(\)\s*\{([^{}]*)\}', obj_init, src)
+    src = re.sub(r'new\s+(Dictionary<[^>]*>)\s*\(', r'\1(', src)
+    src = re.sub(r'new\s+(ArgumentException)\s*\(', r'\1(', src)
+    # reference types -> pointers
+    cls = '|'.join(REF_CLASSES)
+    src = re.sub(r'new\s+(%s)\[([^\]]+)\]' % cls, r'Arr<\1*>::New(\2)', src)
+    src = re.sub(r'\b(%s)\[\]' % cls, r'Arr<\1*>', src)
+    src = re.sub(r'(?<!struct )(?<!new )\b(%s)[ \t]+(\w+)[ \t]*(?=[=;,)])' % cls, r'\1* \2', src)   # (same line only: comments name classes too)
+    src = re.sub(r'\bStream[ \t]+(\w+)[ \t]*(?=[=;,)])', r'CsStream* \1', src)
+    src = re.sub(r'<int,\s*(%s)>' % cls, r'<int, \1*>', src)
+    src = re.sub(r'\(\((%s)\)(\w+)\)\.' % cls, r'((\1*)\2)->', src)
+    src = re.sub(r'foreach\s*\(\s*(%s)\s+(\w+)\s+in\s+([\w.]+)\s*\)' % cls, r'for (\1* \2 : \3())', src)
+    # C++ does not let a goto jump over an initialised declaration in the same scope; split it (no logic changes)
+    src = re.sub(r'\b((?:%s)\*) (\w+)\s*=\s*null;' % cls, r'\1 \2; \2 = null;', src)
+    src = re.sub(r'\b(%s)\.' % '|'.join(PTR_VARS), r'\1->', src)
+    src = re.sub(r'\b(KeyFrames|Streams)\[([^\]]+)\]\.', r'\1[\2]->', src)
+    # out parameters: like ref
+    src = re.sub(r'\bout\s+(\w+)\s+(\w+)', r'\1& \2', src)
+    src = re.sub(r'\bout\s+(\w+)\s*([,)])', r'\1\2', src)
+    src = re.sub(r'\bEncoding\.', 'Encoding::', src)
+    src = re.sub(r'\bString\b', 'CsString', src)
+    src = close_structs(cs_to_cpp(src))
+    # C# zero-initialises fields (and demands definite assignment of locals): declarations without an initialiser get `{}`
+    src = re.sub(r'^([ \t]+)((?!return\b|goto\b|throw\b|typedef\b|using\b|struct\b|else\b|delete\b|case\b|break\b|continue\b)[\w:]+(?:<[^;()]*>)?\*?)[ \t]+(\w+);[ \t]*(//[^\n]*)?$',
+                 r'\1\2 \3{};', src, flags=re.M)
     return src
 
 
@@ -158,6 +244,17 @@ def main():
         enc = enc.replace('int newval = val -', 'int newval; newval = val -')
         f.write('\ntypedef LibMobiclip_Codec_Mobiclip::BitWriter& BitWriterRef;\n')
         f.write(cs_to_cpp('namespace LibMobiclip.Codec.Mobiclip.Encoder\n{\n    public class EncEntropy\n    {\n%s\n    }\n}\n' % enc))
+    # Containers: ModsDemuxer (whole file), the MoLive demuxer with its chunk classes and bit reader, and the reference's own
+    # Moflex MUXER base class (an independent writer for the files the demuxers are tested on).
+    cont = ['Moflex/MoLive.cs', 'Moflex/MoLiveInBitStream.cs', 'Moflex/MoLiveChunk.cs', 'Moflex/MoLiveStream.cs', 'Moflex/MoLiveStreamCodec.cs',
+            'Moflex/MoLiveStreamVideo.cs', 'Moflex/MoLiveStreamVideoWithLayout.cs', 'Moflex/MoLiveStreamAudio.cs', 'Moflex/MoLiveStreamTimeline.cs',
+            'Moflex/MoLiveChunkFoo.cs', 'Moflex/MoLiveDemux.cs', 'Moflex/MoflexMuxer.cs', 'Mods/ModsDemuxer.cs']
+    with open(os.path.join(OUT, 'gen_Containers.h'), 'w') as f:
+        f.write('// transliterated at build time from the reference -- NOT committed, do not edit\n')
+        for rel in cont:
+            cs = open(os.path.join(REF, 'LibMobiclip/Containers', rel), encoding='utf-8-sig').read()
+            f.write('\n// ---- %s ----\n' % rel)
+            f.write(cs_container_to_cpp(cs))
     so = os.path.join(OUT, 'libmobiref.so')
     cmd = ['g++', '-std=c++17', '-O2', '-fPIC', '-shared', '-fwrapv', '-ffp-contract=off', '-fno-strict-aliasing',
            '-w', '-fpermissive', '-fmax-errors=30', '-I', HERE, '-I', OUT, os.path.join(HERE, 'ref_capi.cpp'), '-o', so]

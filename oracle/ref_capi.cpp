@@ -195,3 +195,111 @@ int mobiref2_bw_bytes(void* h, uint8_t* out, int cap) {
 }
 }  // extern "C"
 
+
+// ---- containers (tests/test_containers_vs_ref.py): the reference's ModsDemuxer, MoLiveDemux and MoflexMuxer ----------------
+#include "gen_Containers.h"
+using LibMobiclip_Containers_Mods::ModsDemuxer;
+using namespace LibMobiclip_Containers_Moflex;
+
+extern "C" {
+
+struct RefMods { CsStream s; ModsDemuxer* d = nullptr; Arr<byte> last; };
+// new ModsDemuxer(stream).  Returns null when the reference throws (tables outside the file ...).
+void* mobiref_mods_open(const uint8_t* data, size_t len) {
+    RefMods* r = new RefMods();
+    r->s = CsStream(data, len);
+    try { r->d = new ModsDemuxer(&r->s); } catch (...) { delete r; return nullptr; }
+    return r;
+}
+void mobiref_mods_close(void* h) { delete (RefMods*)h; }
+// the 0x30-byte header as 14 u32 (magic as its four bytes, little endian)
+void mobiref_mods_header(void* h, uint32_t* out) {
+    ModsDemuxer::ModsHeader* H = ((RefMods*)h)->d->Header;
+    uint32_t magic = 0;
+    for (int i = 0; i < 4 && i < (int)H->ModsString.size(); i++) magic |= (uint32_t)(uint8_t)H->ModsString[(size_t)i] << (8 * i);
+    const uint32_t v[14] = {magic, H->TagId, H->TagIdSizeDword, H->FrameCount, H->Width, H->Height, H->Fps, H->AudioCodec, H->NbChannel,
+                            H->Frequency, H->BiggestFrame, H->AudioOffset, H->KeyframeIndexOffset, H->KeyframeCount};
+    std::memcpy(out, v, sizeof v);
+}
+int mobiref_mods_keyframe(void* h, uint32_t i, uint32_t* frame_number, uint32_t* data_offset) {
+    ModsDemuxer* d = ((RefMods*)h)->d;
+    if ((long long)i >= d->KeyFrames.Length) return -1;
+    *frame_number = d->KeyFrames[i]->FrameNumber; *data_offset = d->KeyFrames[i]->DataOffset;
+    return 0;
+}
+// ReadFrame(out NrAudioPackets, out IsKeyFrame): 1 and a view of the packet, 0 when it returned null, -1 when it threw
+int mobiref_mods_read_frame(void* h, const uint8_t** frame, uint32_t* len, uint32_t* nr_audio, int* is_key) {
+    RefMods* r = (RefMods*)h;
+    try {
+        uint na = 0; bool key = false;
+        r->last = r->d->ReadFrame(na, key);
+        if (!r->last.p) return 0;
+        *frame = r->last.raw(); *len = (uint32_t)r->last.Length; *nr_audio = na; *is_key = key ? 1 : 0;
+        return 1;
+    } catch (...) { return -1; }
+}
+
+struct RefFrame { MoLiveChunk* chunk; Arr<byte> data; };
+struct RefMoflex { CsStream s; MoLiveDemux* d = nullptr; std::vector<RefFrame> q; size_t head = 0; };
+void* mobiref_moflex_open(const uint8_t* data, size_t len) {
+    RefMoflex* r = new RefMoflex();
+    r->s = CsStream(data, len);
+    r->d = new MoLiveDemux(&r->s);
+    r->d->OnCompleteFrameReceived = [r](MoLiveChunk* c, Arr<byte> d) { r->q.push_back(RefFrame{c, d}); };
+    return r;
+}
+void mobiref_moflex_close(void* h) { delete (RefMoflex*)h; }
+// ReadPacket(): its return value; 0xFFFFFFFF when the reference threw (index outside the packet buffer, duplicate stream index)
+uint32_t mobiref_moflex_read_packet(void* h) {
+    RefMoflex* r = (RefMoflex*)h;
+    try { return r->d->ReadPacket(); } catch (...) { return 0xFFFFFFFFu; }
+}
+long long mobiref_moflex_position(void* h) { return ((RefMoflex*)h)->s.Position; }
+// Oldest frame OnCompleteFrameReceived delivered: the chunk's fields as 14 u32 in the order of mobi_moflex_stream
+int mobiref_moflex_next_frame(void* h, uint32_t* st, const uint8_t** data, uint32_t* len) {
+    RefMoflex* r = (RefMoflex*)h;
+    if (r->head >= r->q.size()) return 0;
+    RefFrame& f = r->q[r->head++];
+    uint32_t v[14] = {0};
+    v[1] = f.chunk->Id;
+    if (f.chunk->IsStream()) v[0] = (uint32_t)((MoLiveStream*)f.chunk)->StreamIndex;
+    if (f.chunk->Id == 1 || f.chunk->Id == 3) {
+        MoLiveStreamVideo* c = (MoLiveStreamVideo*)f.chunk;
+        v[2] = c->CodecId; v[3] = c->FpsRate; v[4] = c->FpsScale; v[5] = c->Width; v[6] = c->Height; v[7] = c->PelRatioRate; v[8] = c->PelRatioScale;
+        if (f.chunk->Id == 3) { MoLiveStreamVideoWithLayout* w = (MoLiveStreamVideoWithLayout*)f.chunk; v[9] = (uint32_t)w->ImageLayout; v[10] = w->ImageRotation; }
+    } else if (f.chunk->Id == 2) {
+        MoLiveStreamAudio* c = (MoLiveStreamAudio*)f.chunk;
+        v[2] = c->CodecId; v[11] = c->Frequency; v[12] = c->Channel;
+    } else if (f.chunk->Id == 4) v[13] = ((MoLiveStreamTimeline*)f.chunk)->AssociatedStreamIndex;
+    std::memcpy(st, v, sizeof v);
+    *data = f.data.raw(); *len = (uint32_t)f.data.Length;
+    return 1;
+}
+
+// The reference's MoflexMuxer (MoflexMuxer.cs:11-96) as a writer
+struct RefMux { CsStream s; MoflexMuxer* m = nullptr; };
+void* mobiref_mux_create(void) { RefMux* r = new RefMux(); r->m = new MoflexMuxer(&r->s); return r; }
+void mobiref_mux_destroy(void* h) { delete (RefMux*)h; }
+void mobiref_mux_synchro_header(void* h) { ((RefMux*)h)->m->WriteSynchroHeader(); }
+void mobiref_mux_video_chunk(void* h, uint32_t fps_rate, uint32_t fps_scale, uint32_t w, uint32_t hh, uint32_t par, uint32_t pas, int stream_index, uint32_t codec) {
+    MoLiveStreamVideo* c = new MoLiveStreamVideo(fps_rate, fps_scale, w, hh, par, pas);
+    c->StreamIndex = stream_index; c->CodecId = codec;
+    ((RefMux*)h)->m->WriteSynchroChunk(c);
+}
+void mobiref_mux_end_chunks(void* h) { ((RefMux*)h)->m->WriteSynchroChunk(nullptr); }
+void mobiref_mux_data_block(void* h) { ((RefMux*)h)->m->WriteDataBlock(); }
+void mobiref_mux_ep(void* h, int ep, const uint8_t* data, int len, int end_frame) {
+    RefMux* r = (RefMux*)h;
+    if (!data) { r->m->WriteEp(ep, nullptr, 0, 0); return; }
+    Arr<byte> a = Arr<byte>::New(len);
+    if (len) std::memcpy(a.raw(), data, (size_t)len);
+    r->m->WriteEp(ep, a, 0, len, end_frame != 0);
+}
+void mobiref_mux_pad(void* h, int n) { RefMux* r = (RefMux*)h; Arr<byte> z = Arr<byte>::New(n); r->s.Write(z, 0, n); }
+size_t mobiref_mux_bytes(void* h, uint8_t* out, size_t cap) {
+    RefMux* r = (RefMux*)h;
+    if (out && cap >= r->s.buf.size()) std::memcpy(out, r->s.buf.data(), r->s.buf.size());
+    return r->s.buf.size();
+}
+
+}  // extern "C"

@@ -217,3 +217,84 @@ def test_moflex_two_streams_fixed_packets_and_counting():
     bad = packet(_ep(0, v[0][:200], False), 7, hdr) + packet(_ep(0, v[0][200:], True), 11) + bytes(PS - 1)
     dm = MoLiveDemux(bad)
     assert [dm.ReadPacket() for _ in range(6)] == [0, 0x50, 0, 0x50, 0, 73]
+
+
+def _layout_file(layout, n=8, second_video=True):
+    """A Moflex file whose video stream is announced by a MoLiveStreamVideoWithLayout chunk (id 3, 13 bytes: the video
+    chunk's 12 + layout | rotation << 4), plus an audio stream and a SECOND video stream the player must ignore."""
+    import struct
+    from container_ref import _ep, _synchro_header, _variable_byte
+    w, h, ver, _ = CONFIGS['moflex_400x240']
+    fr = [d[:-2] for d, _ in frames('moflex_400x240', 77, n)]
+    lay = _variable_byte(3) + _variable_byte(13) + struct.pack('>BBHHHHBB', 0, 0, 30, 1, w, h, 1, 1) + bytes([layout & 15])
+    audio = _variable_byte(2) + _variable_byte(6) + struct.pack('>BB', 1, 0) + (32000 - 1).to_bytes(3, 'big') + bytes([1])
+    other = b''
+    if second_video:
+        other = _variable_byte(1) + _variable_byte(12) + struct.pack('>BBHHHHBB', 1, 0, 30, 1, 64, 48, 1, 1)
+        audio = b''     # end-points 0 and 1 only (MoflexMuxer.WriteEp's byte count is right for those)
+    out = bytearray(_synchro_header() + lay + audio + other + _variable_byte(0) + _variable_byte(0))
+    cap = 0xE00
+    for i, f in enumerate(fr):
+        for at in range(0, len(f), cap):          # one data block per slice; the other stream's frame rides in some of the last ones
+            last = at + cap >= len(f)
+            out += b'\x01' + _ep(0, f[at:at + cap], last) + (_ep(1, b'\x55' * 10, True) if i % 3 == 1 and last else b'') + _ep(0, None, False)
+    out += bytes(0x1000)
+    return bytes(out), fr, (w, h)
+
+
+class _OracleDecoder:
+    """Stand-in with the decoder object's surface, backed by the CPU oracle: lets the player's policy be tested without a GPU."""
+
+    def __init__(self, w, h):
+        self.o, self.Data, self.Offset = Oracle(w, h, 2), None, 0
+
+    def DecodeFrame(self):
+        ok, self.Offset, bgra = self.o.decode(self.Data, self.Offset, True)
+        return bgra if ok else None
+
+
+@pytest.mark.parametrize('layout,is3d', [(0, True), (3, True), (4, True), (6, False)])
+def test_moflex_player_acts_on_image_layout_like_the_reference_player(layout, is3d):
+    """Form1.cs:508-545: every frame of the chosen stream is decoded by ONE decoder; a 3-D layout shows the 1st, 3rd, ... and
+    doubles the frame period; Simple2D (6) shows all; the second video stream and the audio stream are ignored."""
+    from mobiclipdecoder_b200.containers import MoflexPlayer
+    blob, fr, (w, h) = _layout_file(layout)
+    made = []
+    pl = MoflexPlayer(lambda ww, hh: made.append((ww, hh)) or _OracleDecoder(ww, hh))
+    got = list(pl.play(MoLiveDemux(blob)))
+    assert made == [(w, h)] and pl.PlayingVideoStream == 0 and pl.Is3D == is3d
+    assert len(got) == len(fr) and all(g['bitmap'] is not None for g in got)       # the other stream's frames never reach the decoder
+    ref = _OracleDecoder(w, h)
+    for g, f in zip(got, fr):
+        ref.Data, ref.Offset = f + b'\0\0', 0
+        assert np.array_equal(g['bitmap'], ref.DecodeFrame())
+    if is3d:
+        assert [g['present'] for g in got] == [i % 2 == 0 for i in range(len(fr))]
+        assert [g['eye'] for g in got[:4]] == ['left', 'right', 'left', 'right']
+        assert all(g['period_ms'] == pytest.approx(2000.0 / 30) for g in got)
+    else:
+        assert all(g['present'] for g in got) and all(g['period_ms'] == pytest.approx(1000.0 / 30) for g in got)
+
+
+def test_moflex_player_plain_video_chunk_is_2d():
+    from mobiclipdecoder_b200.containers import MoflexPlayer
+    blob, fr, (w, h) = _moflex_file(n=5)
+    pl = MoflexPlayer(_OracleDecoder)
+    got = list(pl.play(MoLiveDemux(blob)))
+    assert not pl.Is3D and len(got) == 5 and all(g['present'] and g['eye'] is None for g in got)
+
+
+@pytest.mark.gpu
+def test_moflex_player_3d_on_gpu():
+    from mobiclipdecoder_b200 import MobiclipDecoder
+    from mobiclipdecoder_b200.containers import MoflexPlayer
+    blob, fr, (w, h) = _layout_file(4, n=10)
+    pl = MoflexPlayer(lambda ww, hh: MobiclipDecoder(ww, hh, 2))
+    ref = _OracleDecoder(w, h)
+    shown = 0
+    for g, f in zip(pl.play(MoLiveDemux(blob)), fr):
+        ref.Data, ref.Offset = f + b'\0\0', 0
+        assert np.array_equal(np.asarray(g['bitmap']).reshape(h, w, 4), ref.DecodeFrame())
+        shown += g['present']
+    assert shown == 5 and pl.Is3D
+    pl.decoder.close()
