@@ -39,6 +39,9 @@ class RefBitWriter:
     def uvar(self, v):
         self.L.mobiref2_bw_uvar(self.h, v)
 
+    def svar(self, v):
+        self.L.mobiref2_bw_svar(self.h, int(v))
+
     def dct(self, levels_in_scan_order):
         a = np.ascontiguousarray(levels_in_scan_order, dtype=np.int32)
         assert self.L.mobiref2_bw_dct(self.h, a.ctypes.data, a.size, 0) == 1
