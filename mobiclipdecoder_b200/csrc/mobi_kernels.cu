@@ -313,10 +313,12 @@ __device__ __forceinline__ uint32_t leaf_word(int x0, int cx0, int mvx, int mvy)
 // mcw, the per-macroblock word that travels by shuffle: bits 0-11 leaf 0, 12-23 leaf 1, then
 constexpr uint32_t MCW_INTER = 1u << 24, MCW_BOX = 1u << 25, MCW_TWO = 1u << 26, MCW_LR = 1u << 27, MCW_SWAP = 1u << 30;   // bits 28-29: first box slot
 
+struct InterTail { uint32_t n_big, first_job, rpp, rpp_magic; };   // see the ticket decoding in k_inter_chunk
+
 template <int LOG2S>
 __global__ void __launch_bounds__(CH_WARPS * 32, 7)
 k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, uint32_t cpp_magic, int mbw, uint32_t mbw_magic, int H,
-              uint32_t* __restrict__ ticket, uint32_t ticket_base, uint32_t prefetch_on,
+              uint32_t* __restrict__ ticket, uint32_t ticket_base, uint32_t prefetch_on, InterTail tail,
               const __grid_constant__ CUtensorMap tm_l, const __grid_constant__ CUtensorMap tm_c4) {
     constexpr int RUN = 4;
     using Smem = RunSmem<RUN>;
@@ -342,17 +344,21 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
     while (t < n_chunks) {
         uint32_t t_next = 0;   // requested now, looked at when this chunk is done
         if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t_next) : "l"(ticket) : "memory");
-        const uint32_t job = __umulhi(t, cpp_magic), chunk = t - job * cpp;
+        // Tickets below tail.n_big are 16-macroblock chunks of pictures 0 .. tail.first_job - 1; the rest are single runs (4
+        // macroblocks) of the last pictures: when the tickets run out, a warp's last piece of work is a quarter as long, so
+        // the SMs drain in a quarter of the time (the launch's tail was ~1/6 of its duration: 5.8 chunks per warp).
+        uint32_t job, mbc, cnt;
+        if (t < tail.n_big) { job = __umulhi(t, cpp_magic); mbc = (t - job * cpp) * CH_MBS; cnt = CH_MBS; }
+        else { const uint32_t t4 = t - tail.n_big, jq = __umulhi(t4, tail.rpp_magic); job = tail.first_job + jq; mbc = (t4 - jq * tail.rpp) * 4u; cnt = 4u; }
         const DevJob& J = jobs[job];
         const uint32_t n_mb = J.n_mb;
         if (J.n_intra != n_mb) {   // an I-picture has nothing for this kernel
             // ---- lane-parallel set-up: lanes l and l + 16 look after macroblock mbc + l ----
-            const uint32_t mbc = chunk * CH_MBS;
             if (prefetch_on) {
                 const int fy = (int)__umulhi(mbc, mbw_magic);
-                prefetch_chunk_region<LOG2S>(J.ref[0], H, mbw, (int)mbc - fy * mbw, fy, (int)min((uint32_t)CH_MBS, n_mb - mbc), lane);
+                prefetch_chunk_region<LOG2S>(J.ref[0], H, mbw, (int)mbc - fy * mbw, fy, (int)min(cnt, n_mb - mbc), lane);
             }
-            const bool in = mbc + k16 < n_mb;
+            const bool in = (uint32_t)k16 < cnt && mbc + k16 < n_mb;
             const uint32_t mbk = in ? mbc + k16 : n_mb - 1;
             const uint4 d = __ldg(reinterpret_cast<const uint4*>(J.mbs + mbk));
             const uint32_t* const coefs = reinterpret_cast<const uint32_t*>(J.coefs);
@@ -405,7 +411,7 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
 
 #pragma unroll 1
             for (int r = 0; r < CH_MBS / RUN; r++) {
-                if (mbc + (uint32_t)(RUN * r) >= n_mb) break;
+                if ((uint32_t)(RUN * r) >= cnt || mbc + (uint32_t)(RUN * r) >= n_mb) break;
                 const int l0 = RUN * r;              // lanes l0 .. l0+3 hold this run's macroblocks
                 const bool mine = (k16 >> 2) == r;
                 // everyone is done with the previous run's shared memory; its generic-proxy traffic is ordered before the boxes
@@ -1392,7 +1398,22 @@ cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const InterMaps
     const uint32_t warps = choice == 0 ? CH_WARPS : V3_WARPS;
     uint32_t ctas = (uint32_t)sm_count * (choice == 0 ? 7u : (uint32_t)(choice >> 1));
     if (ctas > (n_chunks + warps - 1) / warps) ctas = (n_chunks + warps - 1) / warps;
-#define MOBI_LAUNCH(K) K<<<ctas, warps * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, tickets, ticket_base[0], (exp_flags & 8u) ? 1u : 0u, tm.l3, tm.c4)
+    // k_inter_chunk: the last pictures -- about MOBI_INTER_TAIL (default 1) chunks' worth of macroblocks per resident warp --
+    // are handed out run by run
+    InterTail tail{n_chunks, (uint32_t)n_jobs, 1u, 0u};
+    uint32_t n_tickets = n_chunks;
+    if (choice == 0) {
+        static const float tail_chunks = [] { const char* e = getenv("MOBI_INTER_TAIL"); return e ? (float)atof(e) : 1.0f; }();
+        const uint32_t mb_per_pic = (uint32_t)(g.mbw * g.mbh);
+        uint32_t tail_jobs = (uint32_t)((double)tail_chunks * ctas * warps * CH_MBS / mb_per_pic);
+        if (tail_jobs > (uint32_t)n_jobs) tail_jobs = (uint32_t)n_jobs;
+        tail.first_job = (uint32_t)n_jobs - tail_jobs;
+        tail.n_big = tail.first_job * cpp;
+        tail.rpp = (mb_per_pic + 3u) / 4u;
+        tail.rpp_magic = (uint32_t)((0x100000000ull + (uint64_t)tail.rpp - 1) / (uint64_t)tail.rpp);
+        n_tickets = tail.n_big + tail_jobs * tail.rpp;
+    }
+#define MOBI_LAUNCH(K) K<<<ctas, warps * 32, 0, st>>>(jobs, n_tickets, cpp, cpp_magic, g.mbw, magic, g.H, tickets, ticket_base[0], (exp_flags & 8u) ? 1u : 0u, tail, tm.l3, tm.c4)
 #define MOBI_LAUNCH3(K) K<<<ctas, warps * 32, 0, st>>>(jobs, n_chunks, cpp, cpp_magic, g.mbw, magic, g.H, tm.ring_rows, tickets, ticket_base[0], exp_flags, tm.l2, tm.c3)
 #define MOBI_BY_STRIDE(C, T) do { if (g.log2S == 8) MOBI_LAUNCH3((k_inter_v3<8, C, T>)); else if (g.log2S == 9) MOBI_LAUNCH3((k_inter_v3<9, C, T>)); else MOBI_LAUNCH3((k_inter_v3<10, C, T>)); } while (0)
     switch (choice) {
@@ -1409,7 +1430,7 @@ cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const InterMaps
 #undef MOBI_BY_STRIDE
 #undef MOBI_LAUNCH3
 #undef MOBI_LAUNCH
-    ticket_base[0] += n_chunks + ctas * warps;   // every warp draws exactly one ticket past the end
+    ticket_base[0] += n_tickets + ctas * warps;   // every warp draws exactly one ticket past the end
     if (between) { cudaEventRecord(between[0], st); cudaEventRecord(between[1], st); }
     return cudaGetLastError();
 }
