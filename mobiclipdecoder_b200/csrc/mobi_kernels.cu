@@ -1258,15 +1258,19 @@ __device__ __forceinline__ uint32_t bgra_px(bool moflex, float Y2, float U, floa
     }
     return __byte_perm(__byte_perm(sat_u8(B), sat_u8(G), 0x0040), sat_u8(R) | 0xFF00u, 0x5410);
 }
-// (float)n for 0 <= n < 2^23 minus a bias without the conversion pipe (a quarter of the FP32 rate): 2^23 + n is the float whose
-// low mantissa bits are n.  Exact.
-__device__ __forceinline__ float small_int_to_float(uint32_t n, float bias_plus_2p23) { return __uint_as_float(0x4B000000u | n) - bias_plus_2p23; }
+// (float)(byte k of word) minus a bias in two instructions, one of them on the FP32 pipe: PRMT drops the byte into the low
+// mantissa bits of 2^23, the subtraction removes 2^23 + bias.  Exact.  (Shifts, masks and integer adds run at half the FP32
+// rate on this chip and conversions at a quarter: the kernel is issue-bound, so pixel unpacking is kept off those pipes.)
+template <int K>
+__device__ __forceinline__ float byte_to_float(uint32_t word, float bias_plus_2p23) {
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540 + K)) - bias_plus_2p23;
+}
 
 // Eight pixels per thread: one 64-bit luma load, the five chroma columns the eight pixels touch as one aligned word + one byte
 // per plane (two rows of them on odd lines), two 16-byte stores.  Width is a multiple of 16, so a picture row is W / 8 threads.
 // The reference averages chroma in float -- (c - 128) summed over the 1, 2 or 4 samples a pixel uses, divided by their number
-// (MD:269-297); these are sums of small integers and divisions by powers of two, so the same VALUE is formed here from an
-// integer sum with one conversion per pixel and plane.
+// (MD:269-297); these are sums of small integers and divisions by powers of two, exact in binary32 in any order, so the
+// samples are converted once each ((c - 128) straight from the packed word) and summed on the FP32 pipe.
 __global__ void __launch_bounds__(256) k_bgra(const uint8_t* const* __restrict__ srcs, uint8_t* __restrict__ dst, int pitch, size_t per, Geom g, uint32_t wo_magic) {
     const int wo = g.W >> 3;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1281,33 +1285,36 @@ __global__ void __launch_bounds__(256) k_bgra(const uint8_t* const* __restrict__
     const bool last8 = x + 8 >= g.W, lasty = y == g.H - 1;
     const bool below = (y & 1) && !lasty;
     const uint32_t uw = *reinterpret_cast<const uint32_t*>(C), vw = *reinterpret_cast<const uint32_t*>(C + h);
-    uint32_t u[5], v[5];
-#pragma unroll
-    for (int c = 0; c < 4; c++) { u[c] = (uw >> (8 * c)) & 255u; v[c] = (vw >> (8 * c)) & 255u; }
-    u[4] = last8 ? 0u : C[4]; v[4] = last8 ? 0u : C[h + 4];
-    const uint32_t u3top = u[3], v3top = v[3];   // (the last column's odd pixel uses its own sample only, even on an odd line)
+    constexpr float BC = 8388608.0f + 128.0f;
+    float u[5], v[5];
+    u[0] = byte_to_float<0>(uw, BC); u[1] = byte_to_float<1>(uw, BC); u[2] = byte_to_float<2>(uw, BC); u[3] = byte_to_float<3>(uw, BC);
+    v[0] = byte_to_float<0>(vw, BC); v[1] = byte_to_float<1>(vw, BC); v[2] = byte_to_float<2>(vw, BC); v[3] = byte_to_float<3>(vw, BC);
+    u[4] = last8 ? 0.0f : byte_to_float<0>(C[4], BC); v[4] = last8 ? 0.0f : byte_to_float<0>(C[h + 4], BC);
+    const float u3top = u[3], v3top = v[3];   // (the last column's odd pixel uses its own sample only, even on an odd line)
     if (below) {
         const uint32_t ub = *reinterpret_cast<const uint32_t*>(C + S), vb = *reinterpret_cast<const uint32_t*>(C + S + h);
-#pragma unroll
-        for (int c = 0; c < 4; c++) { u[c] += (ub >> (8 * c)) & 255u; v[c] += (vb >> (8 * c)) & 255u; }
-        if (!last8) { u[4] += C[S + 4]; v[4] += C[S + h + 4]; }
+        u[0] += byte_to_float<0>(ub, BC); u[1] += byte_to_float<1>(ub, BC); u[2] += byte_to_float<2>(ub, BC); u[3] += byte_to_float<3>(ub, BC);
+        v[0] += byte_to_float<0>(vb, BC); v[1] += byte_to_float<1>(vb, BC); v[2] += byte_to_float<2>(vb, BC); v[3] += byte_to_float<3>(vb, BC);
+        if (!last8) { u[4] += byte_to_float<0>(C[S + 4], BC); v[4] += byte_to_float<0>(C[S + h + 4], BC); }
     }
     // samples per pixel: even x -> 1 (2 on odd lines), odd x -> twice that, except in the last row / column (none but its own)
-    const float k1 = below ? 0.5f : 1.0f, b1 = below ? 8388608.0f + 256.0f : 8388608.0f + 128.0f;   // even x: scale, 2^23 + 128 * samples
+    const float k1 = below ? 0.5f : 1.0f;
     const bool horiz = !lasty;                                                                     // odd x may use its right-hand neighbour
-    const float k2 = horiz ? k1 * 0.5f : 1.0f, b2 = horiz ? (below ? 8388608.0f + 512.0f : 8388608.0f + 256.0f) : 8388608.0f + 128.0f;
+    const float k2 = horiz ? k1 * 0.5f : 1.0f;
     const bool moflex = g.version == MOBI_MOFLEX3DS;
+    float Yf[8];
+    Yf[0] = byte_to_float<0>(yw.x, 8388608.0f); Yf[1] = byte_to_float<1>(yw.x, 8388608.0f); Yf[2] = byte_to_float<2>(yw.x, 8388608.0f); Yf[3] = byte_to_float<3>(yw.x, 8388608.0f);
+    Yf[4] = byte_to_float<0>(yw.y, 8388608.0f); Yf[5] = byte_to_float<1>(yw.y, 8388608.0f); Yf[6] = byte_to_float<2>(yw.y, 8388608.0f); Yf[7] = byte_to_float<3>(yw.y, 8388608.0f);
     uint32_t out[8];
 #pragma unroll
     for (int p = 0; p < 8; p++) {
         const int c = p >> 1;
-        const float Y2 = small_int_to_float(((p < 4 ? yw.x : yw.y) >> (8 * (p & 3))) & 255u, 8388608.0f);
         float U, V;
-        if (!(p & 1)) { U = small_int_to_float(u[c], b1) * k1; V = small_int_to_float(v[c], b1) * k1; }
-        else if (p == 7 && (last8 || !horiz)) { U = small_int_to_float(u3top, 8388608.0f + 128.0f); V = small_int_to_float(v3top, 8388608.0f + 128.0f); }
-        else if (horiz) { U = small_int_to_float(u[c] + u[c + 1], b2) * k2; V = small_int_to_float(v[c] + v[c + 1], b2) * k2; }
-        else { U = small_int_to_float(u[c], b2); V = small_int_to_float(v[c], b2); }   // last row (never an odd line's second row: `below` is off)
-        out[p] = bgra_px(moflex, Y2, U, V);
+        if (!(p & 1)) { U = u[c] * k1; V = v[c] * k1; }
+        else if (p == 7 && (last8 || !horiz)) { U = u3top; V = v3top; }
+        else if (horiz) { U = (u[c] + u[c + 1]) * k2; V = (v[c] + v[c + 1]) * k2; }
+        else { U = u[c]; V = v[c]; }   // last row (never an odd line's second row: `below` is off)
+        out[p] = bgra_px(moflex, Yf[p], U, V);
     }
     uint4* o = reinterpret_cast<uint4*>(dst + per * blockIdx.y + (size_t)y * pitch + (size_t)x * 4);
     o[0] = make_uint4(out[0], out[1], out[2], out[3]);
