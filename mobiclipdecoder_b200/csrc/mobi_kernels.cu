@@ -1256,6 +1256,7 @@ __device__ __forceinline__ uint32_t bgra_px(bool moflex, float Y2, float U, floa
     } else {
         R = (float)((int)Y2 + (int)U - (int)V); G = (float)((int)Y2 + (int)V); B = (float)((int)Y2 - (int)U - (int)V);
     }
+    // (clamp + add 2^23 rounding toward zero + PRMT instead of the saturating conversions was measured: 0.182 vs 0.165 ms)
     return __byte_perm(__byte_perm(sat_u8(B), sat_u8(G), 0x0040), sat_u8(R) | 0xFF00u, 0x5410);
 }
 // (float)(byte k of word) minus a bias in two instructions, one of them on the FP32 pipe: PRMT drops the byte into the low
@@ -1271,6 +1272,7 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, float bias_plus_2p
 // The reference averages chroma in float -- (c - 128) summed over the 1, 2 or 4 samples a pixel uses, divided by their number
 // (MD:269-297); these are sums of small integers and divisions by powers of two, exact in binary32 in any order, so the
 // samples are converted once each ((c - 128) straight from the packed word) and summed on the FP32 pipe.
+template <bool MOFLEX>   // the two colour matrices (MD:300-305 / 309-311) as two kernels: no per-pixel branch, half the code
 __global__ void __launch_bounds__(256) k_bgra(const uint8_t* const* __restrict__ srcs, uint8_t* __restrict__ dst, int pitch, size_t per, Geom g, uint32_t wo_magic) {
     const int wo = g.W >> 3;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1301,7 +1303,6 @@ __global__ void __launch_bounds__(256) k_bgra(const uint8_t* const* __restrict__
     const float k1 = below ? 0.5f : 1.0f;
     const bool horiz = !lasty;                                                                     // odd x may use its right-hand neighbour
     const float k2 = horiz ? k1 * 0.5f : 1.0f;
-    const bool moflex = g.version == MOBI_MOFLEX3DS;
     float Yf[8];
     Yf[0] = byte_to_float<0>(yw.x, 8388608.0f); Yf[1] = byte_to_float<1>(yw.x, 8388608.0f); Yf[2] = byte_to_float<2>(yw.x, 8388608.0f); Yf[3] = byte_to_float<3>(yw.x, 8388608.0f);
     Yf[4] = byte_to_float<0>(yw.y, 8388608.0f); Yf[5] = byte_to_float<1>(yw.y, 8388608.0f); Yf[6] = byte_to_float<2>(yw.y, 8388608.0f); Yf[7] = byte_to_float<3>(yw.y, 8388608.0f);
@@ -1314,7 +1315,7 @@ __global__ void __launch_bounds__(256) k_bgra(const uint8_t* const* __restrict__
         else if (p == 7 && (last8 || !horiz)) { U = u3top; V = v3top; }
         else if (horiz) { U = (u[c] + u[c + 1]) * k2; V = (v[c] + v[c + 1]) * k2; }
         else { U = u[c]; V = v[c]; }   // last row (never an odd line's second row: `below` is off)
-        out[p] = bgra_px(moflex, Yf[p], U, V);
+        out[p] = bgra_px(MOFLEX, Yf[p], U, V);
     }
     uint4* o = reinterpret_cast<uint4*>(dst + per * blockIdx.y + (size_t)y * pitch + (size_t)x * 4);
     o[0] = make_uint4(out[0], out[1], out[2], out[3]);
@@ -1486,7 +1487,8 @@ cudaError_t launch_bgra(const uint8_t* const* srcs, int n, uint8_t* dst, int dst
     const int wo = g.W >> 3, items = wo * g.H;   // eight pixels per thread
     const uint32_t magic = (uint32_t)((0x100000000ull + (uint64_t)wo - 1) / (uint64_t)wo);
     dim3 grid((unsigned)((items + 255) / 256), (unsigned)n);
-    k_bgra<<<grid, 256, 0, st>>>(srcs, dst, dst_pitch, dst_picture_bytes, g, magic);
+    if (g.version == MOBI_MOFLEX3DS) k_bgra<true><<<grid, 256, 0, st>>>(srcs, dst, dst_pitch, dst_picture_bytes, g, magic);
+    else k_bgra<false><<<grid, 256, 0, st>>>(srcs, dst, dst_pitch, dst_picture_bytes, g, magic);
     return cudaGetLastError();
 }
 
