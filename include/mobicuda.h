@@ -93,7 +93,8 @@ typedef struct mobi_coef {
  *   bit  5    a residual follows for this block (its coefficients carry the same blk/sub tags)
  *   bits 6-7  plane 0 Y, 1 U, 2 V
  *   bits 8-9  x/4, bits 10-11 y/4 inside the MB's 16x16 (luma) or 8x8 (chroma) area
- *   bits 16-31 signed plane-predictor delta (modes 2, 12, 20; MD:3019, 3170, 3255) */
+ *   bits 16-31 signed plane-predictor delta (modes 2, 12, 20; MD:3019, 3170, 3255)
+ * A macroblock's ops come in decode order: all luma ops before the chroma ops (MD:1759-1880); at most 27 per macroblock. */
 typedef uint32_t mobi_op;
 
 typedef struct mobi_packed_frame {

@@ -971,26 +971,40 @@ __device__ __forceinline__ void intra_stage_global(const DevJob& J, const Geom& 
     __syncwarp();
 }
 // Run the macroblock's ops in stream order on the staged tiles (fixed block order, each block sees the previous block's
-// reconstruction: MD:1759-1880, 2776-2902).
-__device__ __forceinline__ void intra_ops(const Geom& g, IntraSmem& sm, const IntraItem& it, uint32_t myop, int lane, const int PLANES) {
+// reconstruction: MD:1759-1880, 2776-2902).  Lane k decodes op k ONCE -- where its block sits in the tiles and in the parked
+// residuals, which neighbours exist -- and the loop hands the packed result round by shuffle: the per-op decode was a quarter
+// of the instructions on the wavefront's critical path when every lane repeated it for every op.  Luma ops precede chroma
+// ops in stream order, so a luma-only / chroma-only caller walks its own range only.
+__device__ __forceinline__ void intra_ops(const Geom& g, IntraSmem& sm, const IntraItem& it, uint32_t myop, int lane, const int PLANES, int yoff) {
     const int S = g.S;
     const int n_ops = (int)((it.info >> 2) & 127u);
-    const int mbx = (int)(it.m % (uint32_t)g.mbw), mby = (int)(it.m / (uint32_t)g.mbw);
-    const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
-    for (int k = 0; k < n_ops; k++) {
-        const uint32_t op = __shfl_sync(0xffffffffu, myop, k);
-        const int mode = (int)(op & 31u), plane = (int)((op >> 6) & 3u), x4 = (int)((op >> 8) & 3u), y4 = (int)((op >> 10) & 3u);
-        if (PLANES != 3 && (plane == 0) != (PLANES == 1)) continue;   // the other wavefront's op
-        const bool res = (op >> 5) & 1u;
-        const int delta = (int)(int16_t)(op >> 16);
-        uint8_t* tp; const int16_t* rp; int ts, rs, off;
-        if (plane == 0) { ts = 32; rs = 16; tp = &sm.u.t.y[1 + y4 * 4][4 + x4 * 4]; rp = sm.resid + y4 * 4 * 16 + x4 * 4; off = yoff + y4 * 4 * S + x4 * 4; }
+    const int coff = yoff >> 1;
+    uint32_t mya;   // bits 0-10 tile byte offset of the block, 11-19 residual index, 20-24 mode, 25 residual, 26 left, 27 top, 28 chroma
+    {
+        const uint32_t op = myop;
+        const int plane = (int)((op >> 6) & 3u), x4 = (int)((op >> 8) & 3u), y4 = (int)((op >> 10) & 3u);
+        uint32_t toff, roff; int off;
+        if (plane == 0) { toff = (uint32_t)((1 + y4 * 4) * 32 + 4 + x4 * 4); roff = (uint32_t)(y4 * 4 * 16 + x4 * 4); off = yoff + y4 * 4 * S + x4 * 4; }
         else {
-            ts = 16; rs = 8; tp = &sm.u.t.c[plane - 1][1 + y4 * 4][4 + x4 * 4]; rp = sm.resid + 256 + (plane - 1) * 64 + y4 * 4 * 8 + x4 * 4;
+            toff = (uint32_t)(17 * 32 + (plane - 1) * 9 * 16 + (1 + y4 * 4) * 16 + 4 + x4 * 4); roff = (uint32_t)(256 + (plane - 1) * 64 + y4 * 4 * 8 + x4 * 4);
             off = coff + (plane == 2 ? (S >> 1) : 0) + y4 * 4 * S + x4 * 4;
         }
         const bool left_av = ((off - (plane == 2 ? (S >> 1) : 0)) & (S - 1)) != 0;  // MD:1923, VOffsetfix MD:1885
         const bool top_av = off >= S;                                               // MD:1924
+        mya = toff | roff << 11 | (op & 31u) << 20 | ((op >> 5) & 1u) << 25 | (left_av ? 1u << 26 : 0u) | (top_av ? 1u << 27 : 0u) | (plane ? 1u << 28 : 0u);
+    }
+    // luma ops precede chroma ops (the parser emits them in decode order; mobi_packed_validate insists on it for caller-packed frames)
+    const int n_luma = __popc(__ballot_sync(0xffffffffu, lane < n_ops && !(mya >> 28)));
+    const int k0 = PLANES == 2 ? n_luma : 0, k1 = PLANES == 1 ? n_luma : n_ops;
+    uint8_t* const tiles = &sm.u.t.y[0][0];   // y and c tiles are contiguous (17 x 32, then 2 x 9 x 16)
+    for (int k = k0; k < k1; k++) {
+        const uint32_t a = __shfl_sync(0xffffffffu, mya, k);
+        const int delta = (int)(int16_t)(__shfl_sync(0xffffffffu, myop, k) >> 16);
+        const int mode = (int)((a >> 20) & 31u);
+        const bool res = (a >> 25) & 1u, left_av = (a >> 26) & 1u, top_av = (a >> 27) & 1u, chroma = (a >> 28) & 1u;
+        uint8_t* tp = tiles + (a & 2047u);
+        const int16_t* rp = sm.resid + ((a >> 11) & 511u);
+        const int ts = chroma ? 16 : 32, rs = chroma ? 8 : 16;
         if (mode == 20) intra_predict<16>(tp, ts, 2, delta, left_av, top_av, false, rp, rs, lane);
         else if (mode >= 10) {
             if (mode != 19) intra_predict<4>(tp, ts, mode - 10, delta, left_av, top_av, res, rp, rs, lane);
@@ -1002,10 +1016,9 @@ __device__ __forceinline__ void intra_ops(const Geom& g, IntraSmem& sm, const In
     }
 }
 // Write the macroblock out.
-__device__ __forceinline__ void intra_store(const DevJob& J, const Geom& g, IntraSmem& sm, const IntraItem& it, int lane, const int PLANES) {
+__device__ __forceinline__ void intra_store(const DevJob& J, const Geom& g, IntraSmem& sm, int lane, const int PLANES, int yoff) {
     const int S = g.S;
-    const int mbx = (int)(it.m % (uint32_t)g.mbw), mby = (int)(it.m / (uint32_t)g.mbw);
-    const int yoff = mby * 16 * S + mbx * 16, coff = yoff >> 1;
+    const int coff = yoff >> 1;
     if (PLANES & 1) {
         const int lrow = lane >> 1, lhalf = lane & 1;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.u.t.y[1 + lrow][4 + lhalf * 8]);
@@ -1018,9 +1031,11 @@ __device__ __forceinline__ void intra_store(const DevJob& J, const Geom& g, Intr
     }
 }
 __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g, IntraSmem& sm, const IntraItem& it, uint32_t myop, int lane, const int PLANES) {
+    const int mbx = (int)(it.m % (uint32_t)g.mbw), mby = (int)(it.m / (uint32_t)g.mbw);
+    const int yoff = mby * 16 * g.S + mbx * 16;
     intra_stage_global(J, g, sm, it, lane, PLANES);
-    intra_ops(g, sm, it, myop, lane, PLANES);
-    intra_store(J, g, sm, it, lane, PLANES);
+    intra_ops(g, sm, it, myop, lane, PLANES, yoff);
+    intra_store(J, g, sm, lane, PLANES, yoff);
 }
 
 // Scattered intra macroblocks (those inside P-pictures): persistent warps draw tickets from a dependency-depth-ordered
@@ -1161,7 +1176,7 @@ __device__ __forceinline__ void key_rows(const DevJob& J, const IntraWork* __res
                 }
             }
             __syncwarp();
-            intra_ops(g, sm, it, myop, lane, PLANES);
+            intra_ops(g, sm, it, myop, lane, PLANES, (row * 16) * S + x * 16);
             // ---- hand the macroblock's edges on: next macroblock (register), row below (line buffer) ----
             if (row >= KEY_ROWS && lane == 0) {
                 // the slot still holds the line of row - KEY_ROWS, which row - KEY_ROWS + 1 reads up to a macroblock ahead
@@ -1186,7 +1201,7 @@ __device__ __forceinline__ void key_rows(const DevJob& J, const IntraWork* __res
                 __threadfence_block();      // the line is in shared memory before the counter moves
                 atomicExch(&prog[row], (uint32_t)x + 1u);
             }
-            intra_store(J, g, sm, it, lane, PLANES);
+            intra_store(J, g, sm, lane, PLANES, (row * 16) * S + x * 16);
         }
     }
 }

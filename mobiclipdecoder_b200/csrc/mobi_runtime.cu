@@ -188,6 +188,8 @@ struct PackedValidator {
                     const uint32_t mode = op & 31u, plane = (op >> 6) & 3u, x4 = (op >> 8) & 3u, y4 = (op >> 10) & 3u;
                     const bool res = (op >> 5) & 1u;
                     if (mode > 20 || plane > 2) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op %u mode / plane", m, k);
+                    // decode order (MD:1759-1880): the luma blocks, then chroma; the I-picture kernel's luma and chroma warps each walk their own range
+                    if (k && plane == 0 && ((f.ops[mb.first_sub + k - 1] >> 6) & 3u) != 0) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op %u: luma ops must precede chroma ops", m, k);
                     const uint32_t n4 = mode == 20 ? 4u : mode >= 10 ? 1u : 2u, cells = plane == 0 ? 4u : 2u;   // block and plane width in 4-pixel cells
                     if (x4 + n4 > cells || y4 + n4 > cells) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op %u block outside the macroblock", m, k);
                     if (plane != 0 && (mode == 8 || mode == 18)) return set_err(MOBI_ERR_ARG, "packed frame: MB %u op %u: chroma has no predictor 8 (MD:1866)", m, k);

@@ -140,3 +140,16 @@ def test_partition_geometry_and_vectors():
     p.shape = saved[1]
     keep['mbs'][m].info = (keep['mbs'][m].info & ~(127 << 2))   # no partitions at all
     assert _validate(w, h, ver, pf, pics)[0] == -1
+
+
+def test_luma_ops_must_precede_chroma_ops():
+    """The I-picture kernel's luma and chroma warps each walk their own range of a macroblock's ops (decode order, MD:1759-1880)."""
+    from hand_frames import HandFrame, Mb
+    qtab = [i % 64 | 16 << 8 for i in range(64)] + [i | 16 << 8 for i in range(16)]
+    good = HandFrame(16, 16, 256, qtab, 20, key=True).add(Mb('intra', ops=[(3, 0, 0, 0, 0), (3, 0, 2, 0, 0), (3, 1, 0, 0, 0), (3, 2, 0, 0, 0)]))
+    bad = HandFrame(16, 16, 256, qtab, 20, key=True).add(Mb('intra', ops=[(3, 0, 0, 0, 0), (3, 1, 0, 0, 0), (3, 0, 2, 0, 0), (3, 2, 0, 0, 0)]))
+    pf, keep = good.packed()
+    assert _validate(16, 16, 2, pf, 0)[0] == 0
+    pf, keep = bad.packed()
+    rc, msg = _validate(16, 16, 2, pf, 0)
+    assert rc == -1 and 'luma ops must precede' in msg
