@@ -735,6 +735,39 @@ __device__ __forceinline__ int dir_px(const uint8_t* t, int ts, int mode, int x,
 #undef TT
 #undef LL
 }
+// The diagonal predictors (modes 4-8) without per-lane case analysis.  Every one of them is a two- or three-tap filter sliding
+// along ONE line of neighbours: the left column from the bottom up, the top-left pixel, the top row (and what lies right of
+// it): E(c) = L(-1 - c) for c < 0, TL for c = 0, T(c - 1) for c > 0.  dir_px's cases are then
+//   three taps  F3(c) = (E(c-1) + 2 E(c) + E(c+1) + 2) >> 2        two taps  F2(c) = (E(c) + E(c+1) + 1) >> 1
+//   mode 7  F3(x - y)
+//   mode 5  z = 2y - x, k = y - (x >> 1):  z < 0: F3(-z - 1);  z odd: F3(-k);  z even: F2(-k - 1)
+//   mode 6  z = 2x - y, k = x - (y >> 1):  z < 0: F3(z + 1);   z odd: F3(k);   z even: F2(k)
+//   mode 8  k = x + (y >> 1):              y odd: F3(k + 2);   y even: F2(k + 1)
+//   mode 4  k = y + (x >> 1):              x odd: F3(-2 - k);  x even: F2(-2 - k), with E clamped at its lower end (c >= -N):
+//           that clamp IS the reference's (L(N-2) + 3 L(N-1) + 2) >> 2 and its run of L(N-1) (MD:2141-2200).
+// Lane l holds E(l - N); a pixel fetches its three taps by shuffle: no divergent paths, which were a quarter of the stall
+// samples of the latency-bound I-picture kernel (branch resolution).  dir_px stays as the readable statement (and serves 0, 1).
+template <int N>
+__device__ __forceinline__ int edge_value(const uint8_t* t, int ts, int lane) {
+    const int e = lane - N;
+    constexpr int TOP = N == 8 ? 13 : 7;     // highest coordinate any predictor touches: T(12) for mode 8 (MD:2371-2466), T(6) for mode 18
+    if (e < 0) return t[(-1 - e) * ts - 1];
+    return e <= TOP ? (int)t[-ts + e - 1] : 0;
+}
+template <int N>
+__device__ __forceinline__ int edge_px(int ev, int mode, int x, int y) {
+    int c; bool two;
+    switch (mode) {   // (uniform across the warp)
+    case 4: { const int k = y + (x >> 1); c = -2 - k; two = !(x & 1); break; }
+    case 5: { const int z = 2 * y - x, k = y - (x >> 1); c = z < 0 ? -z - 1 : ((z & 1) ? -k : -k - 1); two = z >= 0 && !(z & 1); break; }
+    case 6: { const int z = 2 * x - y, k = x - (y >> 1); c = z < 0 ? z + 1 : k; two = z >= 0 && !(z & 1); break; }
+    case 7: c = x - y; two = false; break;
+    default: { const int k = x + (y >> 1); c = (y & 1) ? k + 2 : k + 1; two = !(y & 1); break; }
+    }
+    const int l1 = c + N;
+    const int e0 = __shfl_sync(0xffffffffu, ev, max(l1 - 1, 0)), e1 = __shfl_sync(0xffffffffu, ev, max(l1, 0)), e2 = __shfl_sync(0xffffffffu, ev, max(l1 + 1, 0));
+    return two ? (e1 + e2 + 1) >> 1 : (e0 + 2 * e1 + e2 + 2) >> 2;
+}
 // Unclipped plane-predictor value (sub_1167BC MD:3017 for N=16, sub_116CCC MD:3168 for 8, sub_117E98 MD:3253 for 4),
 // the reference's running sums written in closed form (all arithmetic int32, wrap-around like C#).
 template <int N>
@@ -811,13 +844,20 @@ __device__ __forceinline__ void intra_predict(uint8_t* t, int ts, int mode, int 
         // directional predictors: every value is a byte (averages of bytes), so the pixels spread over all 32 lanes --
         // two neighbours per lane, one 16-bit store -- instead of four per lane on half the warp
         const int y = lane >> 2, x = (lane & 3) * 2;
-        uint32_t w = (uint32_t)dir_px<N>(t, ts, mode, x, y) | (uint32_t)dir_px<N>(t, ts, mode, x + 1, y) << 8;
+        uint32_t w;
+        if (mode <= 1) w = (uint32_t)dir_px<N>(t, ts, mode, x, y) | (uint32_t)dir_px<N>(t, ts, mode, x + 1, y) << 8;
+        else {
+            const int ev = edge_value<N>(t, ts, lane);
+            w = (uint32_t)edge_px<N>(ev, mode, x, y) | (uint32_t)edge_px<N>(ev, mode, x + 1, y) << 8;
+        }
         if (res) w = add_res2(w, rp + y * rs + x);
         *reinterpret_cast<uint16_t*>(t + y * ts + x) = (uint16_t)w;
     } else if (N == 4) {
+        const int y = (lane >> 2) & 3, x = lane & 3;
+        int v;
+        if (mode <= 1) v = dir_px<N>(t, ts, mode, x, y);
+        else v = edge_px<N>(edge_value<N>(t, ts, lane), mode, x, y);   // (all lanes take part in the shuffles)
         if (lane < 16) {
-            const int y = lane >> 2, x = lane & 3;
-            int v = dir_px<N>(t, ts, mode, x, y);
             if (res) v = clip255(v + (int)rp[y * rs + x]);
             t[y * ts + x] = (uint8_t)v;
         }
