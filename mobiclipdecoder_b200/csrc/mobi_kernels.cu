@@ -337,6 +337,9 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
     const int lrow = lane >> 1, lhalf = lane & 1;
     const int cpl = lane >> 4, crow = (lane >> 1) & 7;
     const int k16 = lane & 15, k4 = lane & 3;
+    // the kernel launched behind this one (k_intra, as a programmatic dependent) may take the SMs this grid's CTAs give back while
+    // the last tickets are worked off; it waits for this grid's completion before it touches a picture
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     uint32_t t = 0;
     if (lane == 0) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
@@ -1093,6 +1096,10 @@ __global__ void __launch_bounds__(INTRA_WARPS * 32, 8) k_intra(const DevJob* __r
         const IntraItem it = load_item(work + t);
         const DevJob& J = jobs[it.job];
         const uint32_t myop = intra_prefetch<true>(J, sm, it, lane, 3);
+        // Programmatic dependent launch: this grid may start while the inter kernel before it in the stream is still draining
+        // (its CTAs free their SMs one by one over the last tenth of its run).  Everything up to here read only the step's
+        // uploaded arrays; the pictures are touched below, after the inter kernel has completed and flushed.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         // wait for the intra neighbours whose pixels this macroblock's predictors read (host-computed mask)
         if (lane < 4 && ((it.wait >> lane) & 1u)) {
             const int nb = lane == 0 ? (int)it.m - 1 : (int)it.m - g.mbw - 2 + lane;
@@ -1508,9 +1515,16 @@ cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_w
     unsigned cap = (max_warps + INTRA_WARPS - 1) / INTRA_WARPS;
     if (cap < 1) cap = 1;
     if (blocks > cap) blocks = cap;
-    k_intra<<<blocks, INTRA_WARPS * 32, 0, st>>>(jobs, work, n_work, ticket, ticket_base, stamp, g);
+    static const bool pdl = [] { const char* e = getenv("MOBI_PDL"); return !e || atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(INTRA_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_intra, jobs, work, n_work, ticket, ticket_base, stamp, g);
     *warps_launched = blocks * INTRA_WARPS;
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_intra_key(const DevJob* jobs, const IntraWork* work, const void* pics, int n_pics, Geom g, uint32_t* resident, cudaStream_t st) {
