@@ -9,7 +9,7 @@
 //               per-warp shared memory; lane l owns luma row l/2, 8 pixels (one 64-bit store) and 4 chroma pixels;
 //               half-pel filter on packed bytes (truncating averages MD:418-456); residual: eight lanes per coded 8x8
 //               block, transpose through shared memory, saturating pack onto a prediction tile.
-// k_intra     : intra macroblocks inside P-pictures, one warp each, drawn by ticket from a dependency-depth-ordered list;
+// k_intra     : intra macroblocks inside P-pictures, one warp each, drawn by ticket from a dependency-ordered list (longest chain of dependents first);
 //               the neighbourhood (row above incl. top-right, column left, and the not-yet-decoded pixels to the right,
 //               which the reference reads as 0 from its freshly allocated planes MD:107) is staged in shared memory,
 //               availability decided by coordinates, never by memory contents.
@@ -1081,7 +1081,7 @@ __device__ __forceinline__ void intra_reconstruct(const DevJob& J, const Geom& g
     intra_store(J, g, sm, lane, PLANES, yoff);
 }
 
-// Scattered intra macroblocks (those inside P-pictures): persistent warps draw tickets from a dependency-depth-ordered
+// Scattered intra macroblocks (those inside P-pictures): persistent warps draw tickets from a dependency-ordered
 // list; completion is published as a per-macroblock stamp in global memory.
 __global__ void __launch_bounds__(INTRA_WARPS * 32, 8) k_intra(const DevJob* __restrict__ jobs, const IntraWork* __restrict__ work, uint32_t n_work,
                                                            uint32_t* ticket, uint32_t ticket_base, uint32_t stamp, Geom g) {
@@ -1509,7 +1509,7 @@ cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_w
                          uint32_t stamp, Geom g, uint32_t max_warps, cudaStream_t st, uint32_t* warps_launched) {
     *warps_launched = 0;
     if (n_work == 0) return cudaSuccess;
-    // Tickets are handed out in dependency-depth order, so a warp only ever waits for tickets drawn before its own,
+    // Tickets are handed out in dependency order (whoever is awaited holds an earlier ticket), so a warp only ever waits for tickets drawn before its own,
     // which are held by warps that are already running: any grid size makes progress.
     unsigned blocks = (unsigned)((n_work + INTRA_WARPS - 1) / INTRA_WARPS);
     unsigned cap = (max_warps + INTRA_WARPS - 1) / INTRA_WARPS;

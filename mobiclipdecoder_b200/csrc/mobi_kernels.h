@@ -49,7 +49,7 @@ cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const InterMaps
 // Which inter kernel launch_inter runs (environment: MOBI_INTER_KERNEL), for reports.
 const char* inter_kernel_name();
 // Intra macroblocks (I-frames and intra MBs of P-frames) as a dependency wavefront.  One warp per MB; work is handed
-// out through an atomic ticket in dependency-depth order so that a waiting warp's dependencies are always running.
+// out through an atomic ticket in dependency order (greatest height first) so that a waiting warp's dependencies are always running.
 // *warps_launched receives the number of warps started: each draws exactly one ticket past n_work, so the
 // next launch's ticket_base is ticket_base + n_work + *warps_launched.
 cudaError_t launch_intra(const DevJob* jobs, const IntraWork* work, uint32_t n_work, uint32_t* ticket, uint32_t ticket_base,

@@ -871,6 +871,22 @@ private:
                 per_rank[2 * r] = (uint16_t)(d + 1);
                 per_rank[2 * r + 1] = (uint16_t)wait;
             }
+            // Ticket order.  Depth order (what is awaited first) is a valid order, but it leaves the deepest, mutually dependent
+            // macroblocks for the end of the launch, where nothing else is left to hide their latency (ncu: the SMs idle a
+            // quarter of k_intra's run).  HEIGHT order -- the longest chain of dependents hanging off a macroblock, highest
+            // first -- is a valid order too (whoever is awaited has a greater height than whoever waits, so it holds an earlier
+            // ticket) and ends the launch with the independent leaves.  dep[] is reused: height by macroblock.
+            std::fill(dep.begin(), dep.begin() + h.n_mb, (uint16_t)0);
+            for (uint32_t r = h.n_intra; r-- > 0;) {
+                const int m = (int)f.intra_list[r];
+                const uint32_t wait = per_rank[2 * r + 1];
+                for (int b = 0; b < 4; b++) {
+                    if (!((wait >> b) & 1u)) continue;
+                    const int nb = b == 0 ? m - 1 : m - g_.mbw - 2 + b;
+                    if (dep[nb] < dep[m] + 1) dep[nb] = (uint16_t)(dep[m] + 1);
+                }
+            }
+            for (uint32_t r = 0; r < h.n_intra; r++) per_rank[2 * r] = dep[f.intra_list[r]];   // height; turned into a sort key below
         });
         {
             uint32_t maxd = 0;
@@ -879,12 +895,17 @@ private:
                 const uint16_t* per_rank = depth_[j].data() + h.n_mb;
                 for (uint32_t r = 0; r < h.n_intra; r++) if (per_rank[2 * r] > maxd) maxd = per_rank[2 * r];
             }
-            // P-pictures' intra macroblocks: counting sort by depth.  I-pictures: raster order per picture (the row kernel
+            for (int j = 0; j < L.n_jobs; j++) {   // sort key: greatest height first
+                const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr;
+                uint16_t* per_rank = depth_[j].data() + h.n_mb;
+                for (uint32_t r = 0; r < h.n_intra; r++) per_rank[2 * r] = (uint16_t)(maxd - per_rank[2 * r]);
+            }
+            // P-pictures' intra macroblocks: counting sort by that key.  I-pictures: raster order per picture (the row kernel
             // indexes work[work_base + m]), pictures one after the other behind the P list.
             // One CTA per I-picture suits the few I-pictures of a staggered step (they hide behind the inter kernel on a few
             // SMs).  A step with more I-pictures than SMs would run them in waves of one picture-latency each (measured: 1024
             // pictures, 7 waves, 2.0 ms); such a step is throughput-bound, not latency-bound, and its macroblocks go through
-            // the depth-ordered ticket list with everything else (all pictures' wavefronts advance together).
+            // the dependency-ordered ticket list with everything else (all pictures' wavefronts advance together).
             int n_ipics = 0;
             for (int j = 0; j < L.n_jobs; j++) { const mobi_frame_hdr& h = *views_[L.job_stream[j]].hdr; if (h.n_intra == h.n_mb) n_ipics++; }
             const bool ipics_by_ticket = n_ipics > key_ticket_threshold_;
