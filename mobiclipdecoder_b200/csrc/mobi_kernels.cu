@@ -1142,6 +1142,13 @@ struct KeyShared {   // behind the KEY_WARPS per-warp IntraSmem blocks
 };
 __host__ __device__ inline size_t key_smem_bytes(int S) { return KEY_WARPS * sizeof(IntraSmem) + sizeof(KeyShared) + 2 * (size_t)KEY_ROWS * (size_t)S; }
 
+// Wait until a row's progress counter (shared memory) reaches `need`.  A picture takes well under a millisecond; 2^24 polls of
+// >= 20 ns each can only mean a broken dependency table, and a trap is a reported error where a hang would take the GPU along.
+__device__ __forceinline__ void key_wait(uint32_t* counter, uint32_t need) {
+    uint32_t polls = 0;
+    while (atomicAdd(counter, 0u) < need) { __nanosleep(20); if (++polls > (1u << 24)) __trap(); }
+}
+
 // PLANES is a run-time value here on purpose: one copy of the (large) intra code serves both wavefronts, and the
 // instruction cache is what a handful of latency-bound warps live on.
 __device__ __forceinline__ void key_rows(const DevJob& J, const IntraWork* __restrict__ items, const Geom& g, IntraSmem& sm, KeyShared& ks, uint8_t* lines,
@@ -1171,8 +1178,8 @@ __device__ __forceinline__ void key_rows(const DevJob& J, const IntraWork* __res
                 if (it.wait & 2u) { if (x == 0) need2 = (uint32_t)mbw; else need1 = max(need1, (uint32_t)x); }
                 if (it.wait & 4u) need1 = max(need1, (uint32_t)x + 1u);
                 if ((it.wait & 8u) && x + 1 < mbw) need1 = max(need1, (uint32_t)x + 2u);
-                while (atomicAdd(&prog[row - 1], 0u) < need1) __nanosleep(20);
-                if (need2 && row > 1) while (atomicAdd(&prog[row - 2], 0u) < need2) __nanosleep(20);
+                key_wait(&prog[row - 1], need1);
+                if (need2 && row > 1) key_wait(&prog[row - 2], need2);
                 __threadfence_block();
             }
             __syncwarp();
@@ -1228,7 +1235,7 @@ __device__ __forceinline__ void key_rows(const DevJob& J, const IntraWork* __res
             if (row >= KEY_ROWS && lane == 0) {
                 // the slot still holds the line of row - KEY_ROWS, which row - KEY_ROWS + 1 reads up to a macroblock ahead
                 const uint32_t need = (uint32_t)min(mbw, x + 2);
-                while (atomicAdd(&prog[row - KEY_ROWS + 1], 0u) < need) __nanosleep(20);
+                key_wait(&prog[row - KEY_ROWS + 1], need);
             }
             __syncwarp();
             if (PLANES == 1) {
