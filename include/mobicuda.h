@@ -229,10 +229,11 @@ void mobi_batch_clear_stats(mobi_batch_t* b);
 int mobi_batch_get_phase_times(const mobi_batch_t* b, double ms[4]);
 
 int mobicuda_abi_version(void);
-/* Device-side exhaustive check of the YUV->RGB kernel's division by (255 - 16) (MD:303-305) against IEEE division: every
- * normal float32 of magnitude below 2^18 and zero, both signs.  mismatches[0] receives the number of inputs on which they differ
- * (0 expected), mismatches[1] the bit pattern of the smallest such |x|. */
-int mobicuda_selftest_div239(int device, unsigned long long* mismatches);
+/* Device-side exhaustive check of the YUV->RGB kernel's Moflex colour arithmetic (MD:300-305): the kernel evaluates a cheaper
+ * expression than the reference's float sequence; for EVERY possible input -- Y 0..255, U and V the 1021 multiples of 1/4 in
+ * [-128, 127], 267 M triples -- the resulting B, G, R, A bytes are compared with those of the reference sequence (IEEE division
+ * included).  mismatches[0] receives the number of differing triples (0 expected), mismatches[1] one of them (Y << 20 | u << 10 | v). */
+int mobicuda_selftest_bgra(int device, unsigned long long* mismatches);
 
 #ifdef __cplusplus
 }

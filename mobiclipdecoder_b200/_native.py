@@ -37,7 +37,7 @@ class BatchStats(C.Structure):
 # every symbol include/mobicuda.h declares: name -> (restype, argtypes)
 MOBICUDA_EXPORTS = {
     'mobicuda_abi_version': (C.c_int, []),
-    'mobicuda_selftest_div239': (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong)]),
+    'mobicuda_selftest_bgra': (C.c_int, [C.c_int, C.POINTER(C.c_ulonglong)]),
     'mobi_parser_create': (C.c_int, [C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]),
     'mobi_parser_destroy': (None, [C.c_void_p]),
     'mobi_parser_parse': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(PackedFrame)]),

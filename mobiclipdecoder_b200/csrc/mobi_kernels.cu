@@ -1284,49 +1284,62 @@ __global__ void __launch_bounds__(KEY_WARPS * 32, 1) k_intra_key(const DevJob* _
 // ------------------------------------------------------------------------------------------------
 // YUV -> BGRA (MD:260-323): strict binary32, source order, no contraction (file is built with -fmad=false)
 // ------------------------------------------------------------------------------------------------
-// x / 239 correctly rounded (== __fdiv_rn(x, 239.0f)) in three instructions: q = RN(x * r) with r = RN(1 / 239), the exact
-// remainder x - 239 q by FMA, one correction step (Markstein's division: exact for a correctly rounded reciprocal).  The
-// general-purpose division is about ten instructions with a slow path, three of them per pixel: it made k_bgra
-// compute-bound (0.36 ms per 1024 pictures against 0.09 ms of memory time).  k_div239_selftest compares the two for EVERY
-// float32 of magnitude below 2^18 on the device itself (mobicuda_selftest_div239; tests/test_gpu_parity.py runs it).
-__device__ __forceinline__ float div239(float x) {
-    const float r = 0x1.12358ep-8f;
-    const float q = __fmul_rn(x, r);
-    return __fmaf_rn(__fmaf_rn(-239.0f, q, x), r, q);
-}
-__global__ void k_div239_selftest(unsigned long long* mismatches) {   // [0] count, [1] smallest |x| (bit pattern) that differs
-    // bit patterns 0x00800000 .. 0x487FFFFF are the normal floats below 2^18 (zero is checked too); both signs
-    const uint32_t lo = 0x00800000u, hi = 0x48800000u;
-    unsigned long long bad = 0, first = ~0ull;
-    for (uint32_t i = lo - 1u + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
-        const float x = __uint_as_float(i < lo ? 0u : i);
-        // (bit patterns, except that -0 / 239 comes out as +0: the pixel is clamped at 0 either way)
-        const bool b = i < lo ? (div239(x) != 0.0f || div239(-x) != 0.0f)
-                              : (__float_as_uint(div239(x)) != __float_as_uint(__fdiv_rn(x, 239.0f)) || __float_as_uint(div239(-x)) != __float_as_uint(__fdiv_rn(-x, 239.0f)));
-        if (b) { bad++; if (i < first) first = i; }
-    }
-    if (bad) { atomicAdd(mismatches, bad); atomicMin(mismatches + 1, first); }
-}
-
-// One pixel of the bitmap (MD:262-321) from its luma byte and its (averaged) chroma.  Strict binary32 in source order.
+// One pixel of the bitmap (MD:262-321) from its luma byte and its (averaged) chroma.
 // Clamp to 0..255 and truncation (MD:312-320) are one saturating conversion: cvt.rzi.u8.f32 clamps to the destination's range.
 __device__ __forceinline__ uint32_t sat_u8(float v) {
     uint32_t r;
     asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
     return r;
 }
-__device__ __forceinline__ uint32_t bgra_px(bool moflex, float Y2, float U, float V) {
-    float R, G, B;
-    if (moflex) {
-        R = Y2 + 1.420f * V; G = Y2 - 0.344f * U - 0.714f * V; B = Y2 + 1.772f * U;
-        R = div239((R - 16.0f) * 255.0f);   // (c - 16) * 255 / (255 - 16), MD:303-305; |numerator| < 2^17
-        G = div239((G - 16.0f) * 255.0f);
-        B = div239((B - 16.0f) * 255.0f);
-    } else {
-        R = (float)((int)Y2 + (int)U - (int)V); G = (float)((int)Y2 + (int)V); B = (float)((int)Y2 - (int)U - (int)V);
-    }
+__device__ __forceinline__ uint32_t pack_bgra(float B, float G, float R) {
     // (clamp + add 2^23 rounding toward zero + PRMT instead of the saturating conversions was measured: 0.182 vs 0.165 ms)
     return __byte_perm(__byte_perm(sat_u8(B), sat_u8(G), 0x0040), sat_u8(R) | 0xFF00u, 0x5410);
+}
+// The reference's arithmetic, binary32 in source order (MD:300-305): the statement of what the bytes must be.
+__device__ __forceinline__ uint32_t bgra_px_reference(float Y2, float U, float V) {
+    float R = __fadd_rn(Y2, __fmul_rn(1.420f, V)), G = __fsub_rn(__fsub_rn(Y2, __fmul_rn(0.344f, U)), __fmul_rn(0.714f, V)), B = __fadd_rn(Y2, __fmul_rn(1.772f, U));
+    R = __fdiv_rn(__fmul_rn(__fsub_rn(R, 16.0f), 255.0f), 239.0f);   // (c - 16) * 255 / (255 - 16)
+    G = __fdiv_rn(__fmul_rn(__fsub_rn(G, 16.0f), 255.0f), 239.0f);
+    B = __fdiv_rn(__fmul_rn(__fsub_rn(B, 16.0f), 255.0f), 239.0f);
+    return pack_bgra(B, G, R);
+}
+// What the kernel computes instead.  k_bgra is bound by instruction issue, and 23 of its ~53 instructions per pixel were this
+// arithmetic (three general divisions in round 1: ~45).  The inputs are discrete -- Y is a byte, U and V are multiples of 1/4 in
+// [-128, 127] (one, two or four samples of c - 128 averaged) -- so whether a cheaper expression yields the same BYTE after clamp
+// and truncation is decided by enumeration: 256 x 1021 pairs for R and B, 256 x 1021 x 1021 triples for G
+// (tools/probe/bgra_formula.cu tried a dozen; k_bgra_selftest below repeats the enumeration on the shipped function and
+// tests/test_gpu_parity.py requires zero differences).  What survives:
+//   R, B   two contracted multiply-adds with the constants premultiplied by k+ = the float above 255/239:
+//          fma(V, 1.420f * k+, fma(Y, k+, -16 k+))  -- 2 instructions instead of 7, the inner one shared by R and B
+//   G      the reference's own four matrix operations, then (c - 16) * 255 * r with r = RN(1/239) instead of the division
+//          (every contraction of the G matrix, and k+ on G, changes between 388 and 4693 of the 267 M bytes)
+__device__ __forceinline__ uint32_t bgra_px_moflex(float Y2, float U, float V) {
+    const float KUP = __uint_as_float(0x3f8891adu), M16K = __uint_as_float(0xc18891adu);       // k+, -16 k+
+    const float RV = __uint_as_float(0x3fc1ed94u), BU = __uint_as_float(0x3ff20017u);           // RN(1.420f * k+), RN(1.772f * k+)
+    const float R239 = __uint_as_float(0x3b891ac7u);                                            // RN(1 / 239)
+    const float t = __fmaf_rn(Y2, KUP, M16K);
+    const float R = __fmaf_rn(V, RV, t), B = __fmaf_rn(U, BU, t);
+    const float G = __fmul_rn(__fmul_rn(__fsub_rn(__fsub_rn(__fsub_rn(Y2, __fmul_rn(0.344f, U)), __fmul_rn(0.714f, V)), 16.0f), 255.0f), R239);
+    return pack_bgra(B, G, R);
+}
+// [0] number of (Y, U, V) whose bytes differ between bgra_px_moflex and bgra_px_reference, [1] one such triple (Y << 20 | u << 10 | v)
+__global__ void k_bgra_selftest(unsigned long long* out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 256 * 1021) return;
+    const int yi = idx / 1021, ui = idx - yi * 1021;
+    const float Y = (float)yi, U = (float)(ui - 512) * 0.25f;
+    unsigned long long bad = 0, where = 0;
+    for (int vi = 0; vi < 1021; vi++) {
+        const float V = (float)(vi - 512) * 0.25f;
+        if (bgra_px_moflex(Y, U, V) != bgra_px_reference(Y, U, V)) { bad++; where = (unsigned long long)yi << 20 | (unsigned long long)ui << 10 | (unsigned long long)vi; }
+    }
+    if (bad) { atomicAdd(out, bad); atomicExch(out + 1, where); }
+}
+__device__ __forceinline__ uint32_t bgra_px(bool moflex, float Y2, float U, float V) {
+    if (moflex) return bgra_px_moflex(Y2, U, V);
+    // ModsDS (MD:309-311): integer sums of the truncated values
+    const float R = (float)((int)Y2 + (int)U - (int)V), G = (float)((int)Y2 + (int)V), B = (float)((int)Y2 - (int)U - (int)V);
+    return pack_bgra(B, G, R);
 }
 // (float)(byte k of word) minus a bias in two instructions, one of them on the FP32 pipe: PRMT drops the byte into the low
 // mantissa bits of 2^23, the subtraction removes 2^23 + bias.  Exact.  (Shifts, masks and integer adds run at half the FP32
@@ -1568,13 +1581,12 @@ cudaError_t launch_bgra(const uint8_t* const* srcs, int n, uint8_t* dst, int dst
     return cudaGetLastError();
 }
 
-cudaError_t selftest_div239(unsigned long long* mismatches_host) {
+cudaError_t selftest_bgra(unsigned long long* mismatches_host) {
     unsigned long long* d = nullptr;
     cudaError_t e = cudaMalloc(&d, 2 * sizeof *d);
     if (e != cudaSuccess) return e;
-    const unsigned long long init[2] = {0ull, ~0ull};
-    cudaMemcpy(d, init, sizeof init, cudaMemcpyHostToDevice);
-    k_div239_selftest<<<148 * 16, 256>>>(d);
+    cudaMemset(d, 0, 2 * sizeof *d);
+    k_bgra_selftest<<<(256 * 1021 + 255) / 256, 256>>>(d);
     e = cudaMemcpy(mismatches_host, d, 2 * sizeof *d, cudaMemcpyDeviceToHost);
     cudaFree(d);
     return e;

@@ -65,7 +65,7 @@ cudaError_t launch_gate(const uint32_t* resident, uint32_t target, cudaStream_t 
 cudaError_t launch_bgra(const uint8_t* const* srcs, int n, uint8_t* dst, int dst_pitch, size_t dst_picture_bytes, Geom g, cudaStream_t st);
 // Compares k_bgra's three-instruction division by 239 with __fdiv_rn for every float32 of magnitude below 2^18 (device-side
 // exhaustive check); mismatches_host[0] receives the number of differing results, [1] the bit pattern of the smallest |x| among them.
-cudaError_t selftest_div239(unsigned long long* mismatches_host);
+cudaError_t selftest_bgra(unsigned long long* mismatches_host);
 // Strided planes of n pictures -> tight I420 (n * W*H*3/2 bytes). srcs = device array of luma plane pointers.
 cudaError_t launch_pack_i420(const uint8_t* const* srcs, int n, uint8_t* dst, Geom g, cudaStream_t st);
 

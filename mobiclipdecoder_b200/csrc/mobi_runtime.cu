@@ -1080,10 +1080,10 @@ int mobi_packed_validate(uint32_t width, uint32_t height, int version, const mob
     } catch (...) { return MOBI_ERR_NOMEM; }
 }
 
-int mobicuda_selftest_div239(int device, unsigned long long* mismatches) {
+int mobicuda_selftest_bgra(int device, unsigned long long* mismatches) {
     if (!mismatches) return MOBI_ERR_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return MOBI_ERR_CUDA;
-    return mobi::selftest_div239(mismatches) == cudaSuccess ? MOBI_OK : MOBI_ERR_CUDA;
+    return mobi::selftest_bgra(mismatches) == cudaSuccess ? MOBI_OK : MOBI_ERR_CUDA;
 }
 
 int mobi_create(uint32_t width, uint32_t height, int version, int device, mobi_t** out) {

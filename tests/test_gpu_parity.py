@@ -323,14 +323,15 @@ def test_inter_kernel_variants_agree():
     assert out['split'] == out['v3'] == out['chunk'] == out['v3_8']
 
 
-def test_bgra_division_is_ieee_division_for_every_input():
-    """k_bgra divides by (255 - 16) with a three-instruction sequence instead of the general IEEE division; the library
-    compares the two on the device for every float32 of magnitude below 2^18 (the numerator is below 2^17)."""
+def test_bgra_arithmetic_gives_the_reference_bytes_for_every_input():
+    """k_bgra evaluates a cheaper expression than the reference's float sequence (two contracted multiply-adds for R and B, a
+    multiplication by RN(1/239) instead of the division for G); the library compares the two on the device for every possible
+    (Y, U, V) -- 256 x 1021 x 1021 triples -- and must find no differing byte."""
     import ctypes as C
     from mobiclipdecoder_b200 import _native
     bad = (C.c_ulonglong * 2)(12345, 0)
-    assert _native.mobicuda().mobicuda_selftest_div239(0, bad) == 0
-    assert bad[0] == 0, '%d inputs differ, the smallest has bit pattern 0x%08x' % (bad[0], bad[1])
+    assert _native.mobicuda().mobicuda_selftest_bgra(0, bad) == 0
+    assert bad[0] == 0, '%d triples differ, e.g. Y %d u %d v %d' % (bad[0], bad[1] >> 20, (bad[1] >> 10) & 1023, bad[1] & 1023)
 
 
 @pytest.mark.parametrize('name,w,h', [('mods_256x192', 256, 192), ('moflex_400x240', 400, 240)])
