@@ -193,10 +193,11 @@ __device__ __forceinline__ uint32_t tile_px(const uint8_t* t, int pitch, int pha
 // ------------------------------------------------------------------------------------------------
 // L2 prefetch of a chunk's reference region
 // ------------------------------------------------------------------------------------------------
-// EXPERIMENT (MOBI_INTER_EXP=8), measured and not adopted.  What bounds the inter path is the rate at which the boxes' rows
-// come out of the memory system (tools/probe/tma_rate.cu: a 32x17 box costs 29 SM-cycles when its rows hit L2 and 70-115 when
-// they come from DRAM; the kernels run at 68 cycles per box with half of their sectors missing L2): every box row is its own
-// sector or two, rows lie Stride bytes apart.  Most leaves point into the previous picture close to where they sit, so the
+// EXPERIMENT (MOBI_INTER_EXP=8), measured and not adopted.  One of the two things that bound the inter path (the other is
+// instruction issue: DESIGN.md section 4) is the rate at which the boxes' rows come out of the memory system
+// (tools/probe/tma_rate.cu: a 32x17 box costs 29 SM-cycles when its rows hit L2 and 70-115 when they come from DRAM; the kernel
+// issues 1.9 boxes per macroblock and takes 165 SM-cycles per macroblock with 44 % of its sectors missing L2): every box row
+// is its own sector or two, rows lie Stride bytes apart.  Most leaves point into the previous picture close to where they sit, so the
 // idea was to ask L2, before a warp issues a chunk's boxes, for the whole region of picture 1 the chunk's windows can be
 // expected in, as full 128-byte lines.  Result on the bench mix: DRAM reads 414 -> 517 MB per launch, L2 hit rate unchanged
 // (52 %), kernel 0.263 -> 0.301 ms: the lines a chunk asks for are mostly the ones its neighbours' boxes already brought, and
