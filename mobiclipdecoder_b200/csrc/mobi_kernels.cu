@@ -1312,15 +1312,16 @@ __device__ __forceinline__ uint32_t bgra_px_reference(float Y2, float U, float V
 // tests/test_gpu_parity.py requires zero differences).  What survives:
 //   R, B   two contracted multiply-adds with the constants premultiplied by k+ = the float above 255/239:
 //          fma(V, 1.420f * k+, fma(Y, k+, -16 k+))  -- 2 instructions instead of 7, the inner one shared by R and B
-//   G      the reference's own four matrix operations, then (c - 16) * 255 * r with r = RN(1/239) instead of the division
-//          (every contraction of the G matrix, and k+ on G, changes between 388 and 4693 of the 267 M bytes)
+//   G      the reference's own four matrix operations, then fma(c, 255, -4080) * r with r = RN(1/239) instead of subtraction,
+//          multiplication and division (every contraction of the G matrix, and k+ on G, changes between 128 and 4693 of the
+//          267 M bytes: tools/probe/bgra_formula_g.cu)
 __device__ __forceinline__ uint32_t bgra_px_moflex(float Y2, float U, float V) {
     const float KUP = __uint_as_float(0x3f8891adu), M16K = __uint_as_float(0xc18891adu);       // k+, -16 k+
     const float RV = __uint_as_float(0x3fc1ed94u), BU = __uint_as_float(0x3ff20017u);           // RN(1.420f * k+), RN(1.772f * k+)
     const float R239 = __uint_as_float(0x3b891ac7u);                                            // RN(1 / 239)
     const float t = __fmaf_rn(Y2, KUP, M16K);
     const float R = __fmaf_rn(V, RV, t), B = __fmaf_rn(U, BU, t);
-    const float G = __fmul_rn(__fmul_rn(__fsub_rn(__fsub_rn(__fsub_rn(Y2, __fmul_rn(0.344f, U)), __fmul_rn(0.714f, V)), 16.0f), 255.0f), R239);
+    const float G = __fmul_rn(__fmaf_rn(__fsub_rn(__fsub_rn(Y2, __fmul_rn(0.344f, U)), __fmul_rn(0.714f, V)), 255.0f, -4080.0f), R239);
     return pack_bgra(B, G, R);
 }
 // [0] number of (Y, U, V) whose bytes differ between bgra_px_moflex and bgra_px_reference, [1] one such triple (Y << 20 | u << 10 | v)

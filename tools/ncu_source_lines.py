@@ -48,7 +48,7 @@ def sass_rows(rep, name_part, n_instr):
         title = rows[max(i for i in names if i < hi)][1]
         end = min([i for i in names if i > hi] + [len(rows)])
         body = [r for r in rows[hi + 1:end] if len(r) == len(rows[hi])]
-        name = re.split(r'EPK|ILi', name_part.lstrip('0123456789'))[0]   # mangled fragment -> plain kernel name
+        name = re.split(r'EPK|IL[a-z]', name_part.lstrip('0123456789'))[0]   # mangled fragment -> plain kernel name
         if re.search(r'::%s[(<]' % re.escape(name), title) and len(body) == n_instr:
             return rows[hi], body, title
     raise SystemExit('no launch of %s with %d instructions in %s' % (name_part, n_instr, rep))
