@@ -268,7 +268,7 @@ struct RunSmem {
     uint8_t pad[(128 - (REGION + RUN * TILE + SLOTS * 4 + RUN * 8) % 128) % 128];
 };
 static_assert(sizeof(RunSmem<4>) % 128 == 0, "TMA destinations must stay 128-byte aligned");
-static_assert(sizeof(RunSmem<4>) * 4 + 1024 <= 233472 / 7, "seven 4-warp CTAs per SM");
+static_assert(sizeof(RunSmem<4>) * 4 + 1024 <= 233472 / 7, "up to seven 4-warp CTAs per SM (six are launched: 80 registers per thread measured 1 % faster than seven at 72)");
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -317,7 +317,7 @@ constexpr uint32_t MCW_INTER = 1u << 24, MCW_BOX = 1u << 25, MCW_TWO = 1u << 26,
 struct InterTail { uint32_t n_big, first_job, rpp, rpp_magic; };   // see the ticket decoding in k_inter_chunk
 
 template <int LOG2S>
-__global__ void __launch_bounds__(CH_WARPS * 32, 7)
+__global__ void __launch_bounds__(CH_WARPS * 32, 6)
 k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, uint32_t cpp_magic, int mbw, uint32_t mbw_magic, int H,
               uint32_t* __restrict__ ticket, uint32_t ticket_base, uint32_t prefetch_on, InterTail tail,
               const __grid_constant__ CUtensorMap tm_l, const __grid_constant__ CUtensorMap tm_c4) {
@@ -1488,7 +1488,7 @@ cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const InterMaps
         return cudaGetLastError();
     }
     const uint32_t warps = choice == 0 ? CH_WARPS : V3_WARPS;
-    uint32_t ctas = (uint32_t)sm_count * (choice == 0 ? 7u : (uint32_t)(choice >> 1));
+    uint32_t ctas = (uint32_t)sm_count * (choice == 0 ? 6u : (uint32_t)(choice >> 1));
     if (ctas > (n_chunks + warps - 1) / warps) ctas = (n_chunks + warps - 1) / warps;
     // k_inter_chunk: the last pictures -- about MOBI_INTER_TAIL (default 1) chunks' worth of macroblocks per resident warp --
     // are handed out run by run
