@@ -749,17 +749,17 @@ __device__ __forceinline__ int dir_px(const uint8_t* t, int ts, int mode, int x,
 //   mode 8  k = x + (y >> 1):              y odd: F3(k + 2);   y even: F2(k + 1)
 //   mode 4  k = y + (x >> 1):              x odd: F3(-2 - k);  x even: F2(-2 - k), with E clamped at its lower end (c >= -N):
 //           that clamp IS the reference's (L(N-2) + 3 L(N-1) + 2) >> 2 and its run of L(N-1) (MD:2141-2200).
-// Lane l holds E(l - N); a pixel fetches its three taps by shuffle: no divergent paths, which were a quarter of the stall
-// samples of the latency-bound I-picture kernel (branch resolution).  dir_px stays as the readable statement (and serves 0, 1).
+// A pixel computes its position c on that line and fetches its three taps with three independent loads: no divergent paths,
+// which were a quarter of the stall samples of the latency-bound I-picture kernel (branch resolution).  (Holding E one element
+// per lane and fetching taps by shuffle was measured too: the load -> shuffle chain is longer.)  dir_px stays as the readable
+// statement (and serves 0, 1).
 template <int N>
-__device__ __forceinline__ int edge_value(const uint8_t* t, int ts, int lane) {
-    const int e = lane - N;
-    constexpr int TOP = N == 8 ? 13 : 7;     // highest coordinate any predictor touches: T(12) for mode 8 (MD:2371-2466), T(6) for mode 18
-    if (e < 0) return t[(-1 - e) * ts - 1];
-    return e <= TOP ? (int)t[-ts + e - 1] : 0;
+__device__ __forceinline__ int edge_tap(const uint8_t* t, int ts, int c) {   // E(c), clamped at its lower end
+    c = max(c, -N);
+    return t[c < 0 ? (-1 - c) * ts - 1 : c - ts - 1];
 }
 template <int N>
-__device__ __forceinline__ int edge_px(int ev, int mode, int x, int y) {
+__device__ __forceinline__ int edge_px(const uint8_t* t, int ts, int mode, int x, int y) {
     int c; bool two;
     switch (mode) {   // (uniform across the warp)
     case 4: { const int k = y + (x >> 1); c = -2 - k; two = !(x & 1); break; }
@@ -768,8 +768,7 @@ __device__ __forceinline__ int edge_px(int ev, int mode, int x, int y) {
     case 7: c = x - y; two = false; break;
     default: { const int k = x + (y >> 1); c = (y & 1) ? k + 2 : k + 1; two = !(y & 1); break; }
     }
-    const int l1 = c + N;
-    const int e0 = __shfl_sync(0xffffffffu, ev, max(l1 - 1, 0)), e1 = __shfl_sync(0xffffffffu, ev, max(l1, 0)), e2 = __shfl_sync(0xffffffffu, ev, max(l1 + 1, 0));
+    const int e0 = edge_tap<N>(t, ts, c - 1), e1 = edge_tap<N>(t, ts, c), e2 = edge_tap<N>(t, ts, c + 1);   // three independent loads
     return two ? (e1 + e2 + 1) >> 1 : (e0 + 2 * e1 + e2 + 2) >> 2;
 }
 // Unclipped plane-predictor value (sub_1167BC MD:3017 for N=16, sub_116CCC MD:3168 for 8, sub_117E98 MD:3253 for 4),
@@ -850,18 +849,13 @@ __device__ __forceinline__ void intra_predict(uint8_t* t, int ts, int mode, int 
         const int y = lane >> 2, x = (lane & 3) * 2;
         uint32_t w;
         if (mode <= 1) w = (uint32_t)dir_px<N>(t, ts, mode, x, y) | (uint32_t)dir_px<N>(t, ts, mode, x + 1, y) << 8;
-        else {
-            const int ev = edge_value<N>(t, ts, lane);
-            w = (uint32_t)edge_px<N>(ev, mode, x, y) | (uint32_t)edge_px<N>(ev, mode, x + 1, y) << 8;
-        }
+        else w = (uint32_t)edge_px<N>(t, ts, mode, x, y) | (uint32_t)edge_px<N>(t, ts, mode, x + 1, y) << 8;
         if (res) w = add_res2(w, rp + y * rs + x);
         *reinterpret_cast<uint16_t*>(t + y * ts + x) = (uint16_t)w;
     } else if (N == 4) {
-        const int y = (lane >> 2) & 3, x = lane & 3;
-        int v;
-        if (mode <= 1) v = dir_px<N>(t, ts, mode, x, y);
-        else v = edge_px<N>(edge_value<N>(t, ts, lane), mode, x, y);   // (all lanes take part in the shuffles)
         if (lane < 16) {
+            const int y = lane >> 2, x = lane & 3;
+            int v = mode <= 1 ? dir_px<N>(t, ts, mode, x, y) : edge_px<N>(t, ts, mode, x, y);
             if (res) v = clip255(v + (int)rp[y * rs + x]);
             t[y * ts + x] = (uint8_t)v;
         }
