@@ -271,6 +271,7 @@ public:
         staged_count_.assign(n_streams, 0);
     }
     ~Batch() {
+        if (getenv("MOBI_PACK_TRACE")) fprintf(stderr, "[mobicuda] pack: arena wait %.1f ms, copies %.1f ms, heights %.1f ms, sort %.1f ms (totals since creation; device %d)\n", pack_ms_[0], pack_ms_[1], pack_ms_[2], pack_ms_[3], dev_);
         if (stream_) {
             cudaSetDevice(dev_);
             cudaStreamSynchronize(stream_);
@@ -811,8 +812,10 @@ private:
             if ((int)views_[s].hdr->max_ref > count[s])
                 return set_err(MOBI_ERR_REFERENCE, "stream %d: picture references ring index %u but only %d pictures are decoded", s, views_[s].hdr->max_ref, count[s]);
         }
+        const auto tp0 = std::chrono::steady_clock::now();
         int rc = ensure_arena(a, L.bytes);
         if (rc != MOBI_OK) return rc;
+        const auto tp1 = std::chrono::steady_clock::now();
         DevJob* jobs = reinterpret_cast<DevJob*>(a.h + L.jobs_off);
         const uint8_t** pics = reinterpret_cast<const uint8_t**>(a.h + L.pics_off);
         pool_.run(L.n_jobs, [&](int j) {
@@ -848,6 +851,7 @@ private:
         // macroblocks of equal depth -- of all pictures -- are independent, so the wavefronts of all streams advance
         // together.  Intra macroblocks of P-pictures (shallow, many) and of I-pictures (deep chains, few) go to separate
         // lists: they are launched on different CUDA streams so that the I-picture chains overlap the inter kernel.
+        const auto tp2 = std::chrono::steady_clock::now();
         IntraWork* work = reinterpret_cast<IntraWork*>(a.h + L.work_off);
         depth_.resize(L.n_jobs);
         pool_.run(L.n_jobs, [&](int j) {
@@ -888,6 +892,11 @@ private:
             }
             for (uint32_t r = 0; r < h.n_intra; r++) per_rank[2 * r] = dep[f.intra_list[r]];   // height; turned into a sort key below
         });
+        const auto tp3 = std::chrono::steady_clock::now();
+        pack_ms_[0] += std::chrono::duration<double, std::milli>(tp1 - tp0).count();   // waiting for the arena (the GPU still reads the step before last)
+        pack_ms_[1] += std::chrono::duration<double, std::milli>(tp2 - tp1).count();   // copies into the pinned arena + job table (pool)
+        pack_ms_[2] += std::chrono::duration<double, std::milli>(tp3 - tp2).count();   // dependency heights (pool)
+        struct Tail { double& acc; std::chrono::steady_clock::time_point t; ~Tail() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); } } tail_timer{pack_ms_[3], tp3};   // serial sort
         {
             uint32_t maxd = 0;
             for (int j = 0; j < L.n_jobs; j++) {
@@ -1041,6 +1050,7 @@ private:
     int slot_head_ = 0, slots_used_ = 0;
     mobi_batch_stats stats_{};
     double phase_ms_[4] = {0, 0, 0, 0};
+    double pack_ms_[4] = {0, 0, 0, 0};   // inside `pack`: arena wait, copies + job table, dependency heights, serial sort (MOBI_PACK_TRACE=1 prints them)
     uint32_t quant_override_ = 0, yuv_override_ = 0;
     bool have_override_ = false;
     std::string err_;
