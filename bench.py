@@ -500,6 +500,19 @@ def main():
         lat.sort()
         extra['config3_single_stream_400x240'] = {'frames_per_s': 1e3 * len(lat) / sum(lat), 'latency_ms': {'p50': lat[len(lat) // 2], 'p99': lat[int(len(lat) * 0.99)], 'min': lat[0]},
                                                   'frames': len(lat), 'note': 'mobi_decode_frame + mobi_read_bgra per frame, host buffers, one stream, no batching'}
+        # the same stream with the bitmap of frame k - 1 fetched while frame k is parsed and reconstructed (a player that shows frame k - 1)
+        b1 = MobiBatch(w3, h3, v3, 1, device=local_rank, n_threads=1)
+        for fr in one[:20]:
+            b1.submit([fr], fmt=BGRA); b1.fetch(copy=False)
+        t0 = time.perf_counter()
+        b1.submit([one[20]], fmt=BGRA)
+        for fr in one[21:]:
+            b1.submit([fr], fmt=BGRA)
+            b1.fetch(copy=False)
+        b1.fetch(copy=False)
+        dt = time.perf_counter() - t0
+        b1.close()
+        extra['config3_single_stream_400x240']['pipelined_frames_per_s'] = (len(one) - 20) / dt
     clocks = sampler.stop() if sampler else None
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------------------
