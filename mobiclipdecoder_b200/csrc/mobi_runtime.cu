@@ -283,6 +283,7 @@ public:
             if (out_d_) cudaFree(out_d_);
             if (out_h_) cudaFreeHost(out_h_);
             if (ptr_d_) cudaFree(ptr_d_);
+            if (ring_tab_d_) cudaFree(ring_tab_d_);
             if (ptr_h_) cudaFreeHost(ptr_h_);
             for (int w = 0; w < 5; w++) for (cudaEvent_t e : ev_[w]) cudaEventDestroy(e);
             if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
@@ -327,6 +328,12 @@ public:
             if (!ok(cudaEventCreateWithFlags(&a.consumed, cudaEventDisableTiming), "cudaEventCreate")) return MOBI_ERR_CUDA;
         if (!ok(cudaMalloc(&ptr_d_, sizeof(void*) * (size_t)N_), "cudaMalloc(ptrs)")) return MOBI_ERR_NOMEM;
         if (!ok(cudaMallocHost(&ptr_h_, sizeof(void*) * (size_t)N_), "cudaMallocHost(ptrs)")) return MOBI_ERR_NOMEM;
+        {   // every ring position's address, resident: a single picture is converted without uploading its pointer first
+            std::vector<const uint8_t*> tab((size_t)N_ * RING);
+            for (int s = 0; s < N_; s++) for (int k = 0; k < RING; k++) tab[(size_t)s * RING + k] = picture(s, k);
+            if (!ok(cudaMalloc(&ring_tab_d_, sizeof(void*) * tab.size()), "cudaMalloc(ring table)")) return MOBI_ERR_NOMEM;
+            if (!ok(cudaMemcpy(ring_tab_d_, tab.data(), sizeof(void*) * tab.size(), cudaMemcpyHostToDevice), "H2D ring table")) return MOBI_ERR_CUDA;
+        }
         if (!ok(init_kernel_tables(), "init_kernel_tables")) return MOBI_ERR_CUDA;
         if (!ok(cudaStreamSynchronize(stream_), "init sync")) return MOBI_ERR_CUDA;
         return make_tensor_maps();
@@ -605,9 +612,7 @@ public:
         const size_t per = (size_t)W_ * H_ * 4;
         int rc = ensure_out(per);
         if (rc != MOBI_OK) return rc;
-        ptr_h_[0] = picture(s, count_[s] - 1);
-        if (!ok(cudaMemcpyAsync(ptr_d_, ptr_h_, sizeof(void*), cudaMemcpyHostToDevice, stream_), "H2D ptrs")) return MOBI_ERR_CUDA;
-        if (!ok(launch_bgra(ptr_d_, 1, out_d_, (int)W_ * 4, per, g_, stream_), "k_bgra")) return MOBI_ERR_CUDA;
+        if (!ok(launch_bgra(ring_tab_d_ + (size_t)s * RING + (size_t)((count_[s] - 1) % RING), 1, out_d_, (int)W_ * 4, per, g_, stream_), "k_bgra")) return MOBI_ERR_CUDA;
         stats_.launches++;
         if (!ok(cudaMemcpy2DAsync(dst, (size_t)dst_stride, out_d_, (size_t)W_ * 4, (size_t)W_ * 4, H_, cudaMemcpyDeviceToHost, stream_), "D2H bgra")) return MOBI_ERR_CUDA;
         stats_.d2h_bytes += per;
@@ -1043,6 +1048,7 @@ private:
     uint8_t* out_h_ = nullptr;
     size_t out_cap_ = 0;
     const uint8_t** ptr_d_ = nullptr;
+    const uint8_t** ring_tab_d_ = nullptr;
     const uint8_t** ptr_h_ = nullptr;
     bool timing_ = false;
     std::vector<cudaEvent_t> ev_[5], ev_free_;
