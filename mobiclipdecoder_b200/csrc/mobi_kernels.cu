@@ -314,7 +314,7 @@ __device__ __forceinline__ uint32_t leaf_word(int x0, int cx0, int mvx, int mvy)
 // mcw, the per-macroblock word that travels by shuffle: bits 0-11 leaf 0, 12-23 leaf 1, then
 constexpr uint32_t MCW_INTER = 1u << 24, MCW_BOX = 1u << 25, MCW_TWO = 1u << 26, MCW_LR = 1u << 27, MCW_SWAP = 1u << 30;   // bits 28-29: first box slot
 
-struct InterTail { uint32_t n_big, first_job, rpp, rpp_magic; };   // see the ticket decoding in k_inter_chunk
+struct InterTail { uint32_t n_big, first_job, rpp, rpp_magic, big; };   // see the ticket decoding in k_inter_chunk (big: macroblocks per ordinary ticket, 16 or 8)
 
 template <int LOG2S>
 __global__ void __launch_bounds__(CH_WARPS * 32, 6)
@@ -352,7 +352,7 @@ k_inter_chunk(const DevJob* __restrict__ jobs, uint32_t n_chunks, uint32_t cpp, 
         // macroblocks) of the last pictures: when the tickets run out, a warp's last piece of work is a quarter as long, so
         // the SMs drain in a quarter of the time (the launch's tail was ~1/6 of its duration: 5.8 chunks per warp).
         uint32_t job, mbc, cnt;
-        if (t < tail.n_big) { job = __umulhi(t, cpp_magic); mbc = (t - job * cpp) * CH_MBS; cnt = CH_MBS; }
+        if (t < tail.n_big) { job = __umulhi(t, cpp_magic); mbc = (t - job * cpp) * tail.big; cnt = tail.big; }
         else { const uint32_t t4 = t - tail.n_big, jq = __umulhi(t4, tail.rpp_magic); job = tail.first_job + jq; mbc = (t4 - jq * tail.rpp) * 4u; cnt = 4u; }
         const DevJob& J = jobs[job];
         const uint32_t n_mb = J.n_mb;
@@ -1461,7 +1461,8 @@ cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const InterMaps
     const uint32_t magic = (uint32_t)((0x100000000ull + (uint64_t)g.mbw - 1) / (uint64_t)g.mbw);
     const int choice = inter_kernel_choice();
     static const uint32_t exp_flags = [] { const char* e = getenv("MOBI_INTER_EXP"); return e ? (uint32_t)atoi(e) : 0u; }();   // timing experiments: 1 no residual (wrong pixels), 2 v3 without the multi-leaf box path, 4 k_mc without chroma boxes (wrong pixels), 8 L2 prefetch of the chunk's region
-    const uint32_t chunk_mbs = (choice > 0 && (choice & 1)) ? 8u : 16u;
+    static const bool chunk8 = [] { const char* ch = getenv("MOBI_INTER_CHUNK"); return ch && !strcmp(ch, "8"); }();
+    const uint32_t chunk_mbs = (choice > 0 ? (choice & 1) != 0 : (choice == 0 && chunk8)) ? 8u : 16u;
     const uint32_t cpp = ((uint32_t)(g.mbw * g.mbh) + chunk_mbs - 1) / chunk_mbs, n_chunks = cpp * (uint32_t)n_jobs;
     const uint32_t cpp_magic = (uint32_t)((0x100000000ull + (uint64_t)cpp - 1) / (uint64_t)cpp);
     if (choice < 0) {
@@ -1486,12 +1487,12 @@ cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const InterMaps
     if (ctas > (n_chunks + warps - 1) / warps) ctas = (n_chunks + warps - 1) / warps;
     // k_inter_chunk: the last pictures -- about MOBI_INTER_TAIL (default 1) chunks' worth of macroblocks per resident warp --
     // are handed out run by run
-    InterTail tail{n_chunks, (uint32_t)n_jobs, 1u, 0u};
+    InterTail tail{n_chunks, (uint32_t)n_jobs, 1u, 0u, chunk_mbs};
     uint32_t n_tickets = n_chunks;
     if (choice == 0) {
         static const float tail_chunks = [] { const char* e = getenv("MOBI_INTER_TAIL"); return e ? (float)atof(e) : 1.0f; }();
         const uint32_t mb_per_pic = (uint32_t)(g.mbw * g.mbh);
-        uint32_t tail_jobs = (uint32_t)((double)tail_chunks * ctas * warps * CH_MBS / mb_per_pic);
+        uint32_t tail_jobs = (uint32_t)((double)tail_chunks * ctas * warps * chunk_mbs / mb_per_pic);
         if (tail_jobs > (uint32_t)n_jobs) tail_jobs = (uint32_t)n_jobs;
         tail.first_job = (uint32_t)n_jobs - tail_jobs;
         tail.n_big = tail.first_job * cpp;
