@@ -5,15 +5,19 @@
 // bytes, U in columns [0,Stride/2) and V in [Stride/2,Stride) of each chroma row (MD:107-108, 267-268).
 // Stride padding is zero and never written.
 //
-// k_inter     : one warp per 16x16 inter macroblock.  Reference windows arrive by TMA (the ring is one rank-3 tensor) into
-//               per-warp shared memory; lane l owns luma row l/2, 8 pixels (one 64-bit store) and 4 chroma pixels;
-//               half-pel filter on packed bytes (truncating averages MD:418-456); residual: eight lanes per coded 8x8
-//               block, transpose through shared memory, saturating pack onto a prediction tile.
-// k_intra     : intra macroblocks inside P-pictures, one warp each, drawn by ticket from a dependency-ordered list (longest chain of dependents first);
-//               the neighbourhood (row above incl. top-right, column left, and the not-yet-decoded pixels to the right,
-//               which the reference reads as 0 from its freshly allocated planes MD:107) is staged in shared memory,
-//               availability decided by coordinates, never by memory contents.
-// k_intra_key : I-pictures, one CTA per picture, one warp per macroblock row, progress counters in shared memory.
+// k_inter_chunk : inter macroblocks.  Persistent warps draw 16-macroblock chunks by ticket (the last pictures run by run) and
+//               work them off four macroblocks at a time: reference windows arrive by TMA (the ring is one rank-3 luma
+//               tensor and one rank-4 U|V tensor) into per-warp shared memory, half-pel filter on packed bytes (truncating
+//               averages MD:418-456), the run's coded blocks pooled for the transform passes (eight lanes per 8x8 block),
+//               saturating pack onto prediction tiles, 16-byte stores.  mobi_inter_v3.cuh / mobi_inter_split.cuh hold two
+//               other complete formulations (MOBI_INTER_KERNEL=v3 / split).
+// k_intra     : intra macroblocks inside P-pictures (and of steps with more I-pictures than SMs), one warp each, drawn by
+//               ticket from a dependency-ordered list (longest chain of dependents first); the neighbourhood (row above incl.
+//               top-right, column left, and the not-yet-decoded pixels to the right, which the reference reads as 0 from its
+//               freshly allocated planes MD:107) is staged in shared memory, availability decided by coordinates, never by
+//               memory contents.
+// k_intra_key : I-pictures, one CTA per picture, a luma and a chroma warp per macroblock row, neighbour pixels handed on
+//               through shared memory (line buffers, progress counters).
 // k_bgra / k_pack_i420: output conversions.
 // No tensor cores: these are 8-bit fixed-point butterflies and byte shuffles.
 #include <cstdlib>

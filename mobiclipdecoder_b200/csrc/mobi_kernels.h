@@ -40,10 +40,10 @@ cudaError_t init_kernel_tables();
 //   c3: (Stride/2, 2, rows of all pictures) -- each row split into its U and V halves -- box 32x2x9: the U and the V window of a leaf;
 //   l3 / c4: the same with the picture as a coordinate of its own (what k_inter_chunk takes).
 struct InterMaps { CUtensorMap l2, c3, l3, c4; int ring_rows; };
-// Inter macroblocks of every job: motion compensation from the ring (k_mc), then dequantisation + inverse transforms added in
-// place (k_res); persistent warps drawing chunks of 16 macroblocks through tickets[0] (k_mc) and tickets[16] (k_res), both
-// monotonic like launch_intra's -- ticket_base[0..1] are advanced by what this launch draws.  between[0..1] (optional) are
-// recorded back to back between the two kernels (per-kernel timing: end of k_mc, start of k_res).
+// Inter macroblocks of every job: the fused kernel k_inter_chunk by default; MOBI_INTER_KERNEL=v3 selects k_inter_v3, =split motion
+// compensation (k_mc) followed by dequantisation + inverse transforms added in place (k_res).  Persistent warps draw chunks of
+// macroblocks through tickets[0] (and tickets[16] for k_res), monotonic like launch_intra's -- ticket_base[0..1] are advanced by
+// what this launch draws.  between[0..1] (optional) are recorded back to back after the first kernel (per-kernel timing).
 cudaError_t launch_inter(const DevJob* jobs, int n_jobs, Geom g, const InterMaps& tm, int sm_count, uint32_t* tickets, uint32_t* ticket_base,
                          cudaStream_t st, cudaEvent_t* between);
 // Which inter kernel launch_inter runs (environment: MOBI_INTER_KERNEL), for reports.
@@ -63,8 +63,8 @@ cudaError_t launch_gate(const uint32_t* resident, uint32_t target, cudaStream_t 
 // Y/UV planes of n pictures -> BGRA (MD:260-323). srcs = device array of luma plane pointers; picture i goes to
 // dst + i*dst_picture_bytes with dst_pitch bytes per row.
 cudaError_t launch_bgra(const uint8_t* const* srcs, int n, uint8_t* dst, int dst_pitch, size_t dst_picture_bytes, Geom g, cudaStream_t st);
-// Compares k_bgra's three-instruction division by 239 with __fdiv_rn for every float32 of magnitude below 2^18 (device-side
-// exhaustive check); mismatches_host[0] receives the number of differing results, [1] the bit pattern of the smallest |x| among them.
+// Compares the bytes of k_bgra's Moflex colour arithmetic with those of the reference's float sequence (IEEE division included)
+// for every possible (Y, U, V) on the device; mismatches_host[0] receives the number of differing triples, [1] one of them.
 cudaError_t selftest_bgra(unsigned long long* mismatches_host);
 // Strided planes of n pictures -> tight I420 (n * W*H*3/2 bytes). srcs = device array of luma plane pointers.
 cudaError_t launch_pack_i420(const uint8_t* const* srcs, int n, uint8_t* dst, Geom g, cudaStream_t st);
