@@ -381,10 +381,11 @@ def main():
     roofline = {'bound': 'hbm', 'kernel': inter_name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': ncu_traffic(WORKLOAD, inter_name), 'algorithmic_bytes_per_launch': inter_bytes / n_il, 'launch_ms': inter_ms,
                 'launches_timed': kt['inter_launches'], 'peak_source': peak_src,
-                'step_ms_by_kernel': {inter_name: kt['inter_ms'] / K, 'k_res': kt['res_ms'] / K, 'k_intra_p_pictures': kt['intra_ms'] / K,
+                'step_ms_by_kernel': {inter_name: kt['inter_ms'] / K, 'k_intra_p_pictures': kt['intra_ms'] / K,
                                       'k_intra_i_pictures_side_stream': kt['key_ms'] / K, 'k_bgra': kt['bgra_ms'] / K},
                 'intra_algorithmic_bytes_per_step': intra_bytes / K}
     if not fused and res_ms > 0:
+        roofline['step_ms_by_kernel']['k_res'] = kt['res_ms'] / K
         roofline['inter_path'] = {'kernels': 'k_mc + k_res', 'launch_ms': inter_ms + res_ms, 'algorithmic_bytes_per_launch': (mc_bytes + 4 * d['inter_coefs']) / n_il,
                                   'achieved': ((mc_bytes + 4 * d['inter_coefs']) / n_il) / ((inter_ms + res_ms) * 1e-3) / 1e9}
         roofline['inter_path']['frac'] = roofline['inter_path']['achieved'] / peak
